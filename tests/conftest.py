@@ -1,0 +1,46 @@
+"""
+pytest configuration.
+
+  -m "not gpu"  : CPU suite (oracle vs the reference-generated golden fixtures, host logic,
+                  C-ABI symbol table, gloo world_size-2 sharding logic).
+  -m gpu        : parity tests proper -- the CUDA path, called through the C-ABI library and the
+                  reference-shaped Python API, compared with the oracle on a B200.
+"""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "fp8-mps-metal_b200")
+for p in (ROOT, PKG, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    g = os.path.join(ROOT, "tests", "golden")
+    import json
+    with open(os.path.join(g, "kat.json")) as f:
+        kat = json.load(f)
+    return {
+        "codec": np.load(os.path.join(g, "codec_golden.npz")),
+        "host": np.load(os.path.join(g, "host_golden.npz")),
+        "kat": kat,
+    }
