@@ -1,0 +1,614 @@
+#!/usr/bin/env python3
+"""
+bench.py -- measures the FP8 hot path on B200 and prints ONE JSON line (rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sub]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline (BASELINE.json configs[1], "C2"): `_scaled_mm` GEMV M=1 K=14336 N=4096, bf16 out, HBM-bound.
+  * a STEP is one batch of 128 GEMV calls: 8 passes over a rotation of 16 distinct weight matrices
+    (16 x 58.7 MB = 940 MB, far larger than the 126 MB L2, so every call streams its weights from
+    HBM); the step is captured once in a CUDA graph and replayed, timed with CUDA events on the
+    launching stream after W warm-up replays, barrier + synchronize on both sides, MAX over ranks.
+  * value  = algorithmic bytes of all ranks / time  (58 742 784 B per call), inputs
+             resident in HBM.
+  * e2e    = the same metric through the reference-facing call `torch._scaled_mm(...)` after
+             fp8_mps_patch.install(), with HOST (pinned) buffers: every step copies x and W host->device,
+             runs the op and reads the result back device->host.
+  * roofline = that kernel's algorithmic bytes / its average launch duration over the timed region,
+             against MEASURED_PEAKS.json's copy bandwidth.
+  * cpu_baseline = the oracle port of the reference's CPU path (LUT dequantise + fp32 matmul) on
+             the host cores, bounded sample.
+N > 1: the GEMV does not shard usefully -> independent replicas, weak scaling; the
+N-sharded FLUX linear (C4) + NCCL all-gather is measured in `sub`.
+`sub` carries the other BASELINE configs (C1, C3, C4, C5) with their own rooflines.
+
+--impl reference: the reference's CPU implementation of the same workload (oracle port, all host
+threads), same JSON shape with "impl": "reference".
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "fp8-mps-metal_b200")
+for _p in (PKG, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "FP8 _scaled_mm TFLOPS & M=1 GEMV/cast HBM GB/s as % roofline vs CPU ref"
+
+C2 = dict(M=1, K=14336, N=4096)
+C2_BYTES = 58_742_784
+C1 = dict(M=1, K=4096, N=4096)
+C1_BYTES = 16_789_512
+C3 = dict(M=4, K=4096, N=4096)
+C3_BYTES = 16_834_560
+C4 = dict(M=4096, K=3072, N=12288)
+C4_FLOPS = 309_237_645_312
+ROTATION = 16
+PASSES = 8
+
+FALLBACK_HBM_GBS = 6650.0                  # B200_PROFILING.md fallback
+FALLBACK_BF16_TFLOPS = 1590.0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d["bf16_tflops"]),
+                    bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=FALLBACK_HBM_GBS, bf16=FALLBACK_BF16_TFLOPS, bf16_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Polls NVML for SM clock and throttle reasons while a timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.samples.append((time.perf_counter(), mhz, r))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+
+    def summary(self, t0=None, t1=None):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sel = [s for s in self.samples if (t0 is None or s[0] >= t0) and (t1 is None or s[0] <= t1)] or self.samples
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                 0x100: "display_clock_setting"}
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": int(statistics.median(s[1] for s in sel)), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sel)}
+
+
+# --------------------------------------------------------------------------- helpers
+
+def _capi():
+    from _util import capi
+    return capi()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _mm(L, torch, A, B, C, odt_code, sa, sb, bias=None, bias_dt=0, algo=0):
+    M, K = A.shape
+    N = B.shape[0]
+    rc = L.fp8b_scaled_mm(_ptr(A), _ptr(B), _ptr(C), odt_code, M, N, K, C.stride(0), _ptr(sa), sa.numel(),
+                          _ptr(sb), sb.numel(), _ptr(bias), bias_dt, None, None, 0, algo,
+                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        raise RuntimeError(f"fp8b_scaled_mm failed: {L.fp8b_status_string(rc).decode()} (cuda {L.fp8b_last_cuda_error()})")
+
+
+def _rand_fp8(torch, shape, gen, dev):
+    """randn -> reference-codec FP8 bytes, on the device (fp8b_encode), plus amax/448 scale."""
+    import fp8_mps_native
+    x = torch.randn(shape, generator=gen, device=dev)
+    q, inv = fp8_mps_native.fp8_quantize(x)
+    return q, inv
+
+
+def time_graph(torch, step_fn, steps, warmup, dist=None):
+    """Capture step_fn once, replay: returns (ms_total, launches_per_step, t0, t1 wall-clock marks)."""
+    L = _capi()
+    step_fn()                                     # eager warm-up: lazy attribute setup happens outside capture
+    torch.cuda.synchronize()
+    n0 = L.fp8b_launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step_fn()
+    launches = L.fp8b_launch_count() - n0
+    for _ in range(max(warmup, 3)):
+        g.replay()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1), launches, t0, t1
+
+
+def max_over_ranks(torch, dist, ms):
+    if dist is None:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+
+def cpu_gemv_baseline(seconds_budget=12.0):
+    """The reference's CPU path for C2 on the host cores: (a) numpy LUT dequantise + fp32 BLAS matmul
+    (what test_fp8_metal.py:257-271 does without the MPS hop), (b) the plain-C restatement of the shader
+    loop on all cores.  Reports the faster; bounded to a few calls."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import c_oracle
+    import fp8_oracle as o
+    rng = np.random.default_rng(2)
+    x = o.encode(rng.standard_normal((1, C2["K"])).astype(np.float32) * 50)
+    W = o.encode(rng.standard_normal((C2["N"], C2["K"])).astype(np.float32) * 50)
+    sa = np.array([0.01], np.float32)
+    sb = np.array([0.01], np.float32)
+    res = {}
+    for name, fn in (("c_threads", lambda: c_oracle.scaled_mm(x, W, sa, sb)),
+                     ("numpy_blas", lambda: o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"))):
+        fn()
+        best = float("inf")
+        t_start = time.perf_counter()
+        n = 0
+        while n < 5 and time.perf_counter() - t_start < seconds_budget / 2:
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+            n += 1
+        res[name] = (best, n)
+    pick = min(res, key=lambda k: res[k][0])
+    cores = c_oracle.num_threads() if pick == "c_threads" else (os.cpu_count() or 1)
+    return {"value": round(C2_BYTES / res[pick][0] / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"{res[pick][1]} full-size C2 GEMV calls (M=1 K=14336 N=4096), best; {pick}",
+            "ms_per_call": round(res[pick][0] * 1e3, 3),
+            "alt": {k: round(v[0] * 1e3, 3) for k, v in res.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import c_oracle
+    import fp8_oracle as o
+    rng = np.random.default_rng(2)
+    x = o.encode(rng.standard_normal((1, C2["K"])).astype(np.float32) * 50)
+    W = o.encode(rng.standard_normal((C2["N"], C2["K"])).astype(np.float32) * 50)
+    sa = np.array([0.01], np.float32)
+    sb = np.array([0.01], np.float32)
+    t_c = time.perf_counter(); c_oracle.scaled_mm(x, W, sa, sb); t_c = time.perf_counter() - t_c
+    t_n = time.perf_counter(); o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"); t_n = time.perf_counter() - t_n
+    use_c = t_c <= t_n
+    fn = (lambda: c_oracle.scaled_mm(x, W, sa, sb)) if use_c else \
+        (lambda: o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"))
+    calls_per_step = 2                          # bounded sample of the 128-call step
+    for _ in range(max(args.warmup, 1)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(calls_per_step):
+            fn()
+    dt = time.perf_counter() - t0
+    value = C2_BYTES * calls_per_step * args.steps / dt / 1e9
+    cores = c_oracle.num_threads() if use_c else (os.cpu_count() or 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 _scaled_mm GEMV M=1 K=14336 N=4096 bf16-out, CPU oracle port of the reference path",
+                   "calls_per_step": calls_per_step, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{calls_per_step} full-size C2 calls per step ({'C threads' if use_c else 'numpy LUT + BLAS'})"},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- sub-benchmarks (rank-local)
+
+def bench_gemv_cfg(torch, L, cfg, nbytes, odt, with_bias, gen, dev, peaks, steps, warmup, rotation=ROTATION):
+    from _util import dt_code
+    M, K, N = cfg["M"], cfg["K"], cfg["N"]
+    xs, inv_x = _rand_fp8(torch, (M, K), gen, dev)
+    Ws = []
+    for _ in range(rotation):
+        w, inv_w = _rand_fp8(torch, (N, K), gen, dev)
+        Ws.append(w)
+    bias = torch.randn(N, generator=gen, device=dev).to(odt) if with_bias else None
+    out = torch.empty(M, N, dtype=odt, device=dev)
+    oc = dt_code(odt)
+
+    def step():
+        for w in Ws:
+            _mm(L, torch, xs, w, out, oc, inv_x, inv_w, bias, dt_code(odt) if with_bias else 0)
+
+    ms, launches, _, _ = time_graph(torch, step, steps, warmup)
+    per_call_us = ms * 1e3 / (steps * rotation)
+    gbs = nbytes / (per_call_us * 1e-6) / 1e9
+    # L2-hot variant: one buffer only
+    def step_hot():
+        for _ in range(rotation):
+            _mm(L, torch, xs, Ws[0], out, oc, inv_x, inv_w, bias, dt_code(odt) if with_bias else 0)
+    ms_h, _, _, _ = time_graph(torch, step_hot, steps, warmup)
+    hot_us = ms_h * 1e3 / (steps * rotation)
+    return {"us_per_call": round(per_call_us, 3), "value": round(gbs, 1), "unit": "GB/s",
+            "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": round(gbs / peaks["hbm"], 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
+                         "traffic": None, "peak_source": peaks["source"]},
+            "l2_hot_us_per_call": round(hot_us, 3), "l2_hot_gbs": round(nbytes / (hot_us * 1e-6) / 1e9, 1),
+            "rotation_buffers": rotation, "launches_per_step": launches}
+
+
+def bench_gemm_c4(torch, L, gen, dev, peaks, steps, warmup, n_shard=None, algo=2, sets=4):
+    from _util import dt_code
+    M, K, N = C4["M"], C4["K"], C4["N"]
+    Nl = n_shard or N
+    bufs = []
+    for _ in range(sets):                          # rotation: 4 x (12.6 + 37.7) MB of inputs > 126 MB L2
+        a, inv_a = _rand_fp8(torch, (M, K), gen, dev)
+        w, inv_w = _rand_fp8(torch, (Nl, K), gen, dev)
+        out = torch.empty(M, Nl, dtype=torch.bfloat16, device=dev)
+        bufs.append((a, inv_a, w, inv_w, out))
+
+    def step():
+        for a, inv_a, w, inv_w, out in bufs:
+            _mm(L, torch, a, w, out, dt_code(torch.bfloat16), inv_a, inv_w, algo=algo)
+
+    ms, launches, _, _ = time_graph(torch, step, steps, warmup)
+    us = ms * 1e3 / (steps * sets)
+    flops = 2.0 * M * K * Nl
+    tf = flops / (us * 1e-6) / 1e12
+    fp8_peak_meas = 2 * peaks["bf16"]
+    return {"us_per_call": round(us, 2), "value": round(tf, 1), "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": round(fp8_peak_meas, 1), "unit": "TFLOP/s",
+                         "frac": round(tf / fp8_peak_meas, 4), "frac_of_nominal_4500": round(tf / 4500.0, 4),
+                         "traffic": None, "peak_source": peaks["source"] + " (2 x bf16 cuBLAS burst as dense-FP8 proxy)"},
+            "l2": f"inputs larger than L2: rotation of {sets} (A,B,C) sets, {sets} x 151 MB", "launches_per_step": launches,
+            "shape": [M, K, Nl]}, bufs[0]
+
+
+FLUX_DOUBLE = [(9216, 3072), (3072, 3072), (12288, 3072), (3072, 12288), (18432, 3072)]   # x2 streams x19 blocks
+FLUX_SINGLE = [(21504, 3072), (3072, 15360), (9216, 3072)]                               # x38 blocks
+
+
+def flux_tensor_sizes():
+    sizes = []
+    for _ in range(19):
+        for _ in range(2):
+            sizes += [r * c for r, c in FLUX_DOUBLE]
+    for _ in range(38):
+        sizes += [r * c for r, c in FLUX_SINGLE]
+    return sizes
+
+
+def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
+    """bf16 -> fp8 and fp8 -> fp16 over the whole FLUX-sized weight set, one launch per tensor."""
+    sizes = flux_tensor_sizes()
+    total = sum(sizes)
+    assert total == 11_834_228_736
+    src = torch.empty(total, dtype=torch.bfloat16, device=dev)
+    chunk = 1 << 28
+    for off in range(0, total, chunk):
+        n = min(chunk, total - off)
+        src[off:off + n] = (torch.randn(n, generator=gen, device=dev) * 0.02).to(torch.bfloat16)
+    q = torch.empty(total, dtype=torch.uint8, device=dev)
+    h = torch.empty(total, dtype=torch.float16, device=dev)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def quant():
+        s_ = st()
+        for i, n in enumerate(sizes):
+            rc = L.fp8b_encode(ctypes.c_void_p(src.data_ptr() + 2 * offs[i]), 2, ctypes.c_void_p(q.data_ptr() + offs[i]),
+                               n, None, s_)
+            assert rc == 0
+
+    def dequant():
+        s_ = st()
+        for i, n in enumerate(sizes):
+            rc = L.fp8b_dequant_f16(ctypes.c_void_p(q.data_ptr() + offs[i]), ctypes.c_void_p(h.data_ptr() + 2 * offs[i]),
+                                    n, None, s_)
+            assert rc == 0
+
+    out = {}
+    for name, fn in (("quantize_bf16_to_fp8", quant), ("dequant_fp8_to_fp16", dequant)):
+        ms, launches, _, _ = time_graph(torch, fn, max(3, min(steps, 5)), max(warmup, 3))
+        k = max(3, min(steps, 5))
+        ms_sweep = ms / k
+        gbs = 3.0 * total / (ms_sweep * 1e-3) / 1e9
+        out[name] = {"ms_per_sweep": round(ms_sweep, 3), "value": round(gbs, 1), "unit": "GB/s", "elements": total,
+                     "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                  "frac": round(gbs / peaks["hbm"], 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
+                                  "traffic": None, "peak_source": peaks["source"]},
+                     "launches_per_sweep": launches, "l2": "35.5 GB working set per sweep >> L2"}
+    # spot parity on the last tensor (bit-exact vs the C oracle on a strided sample)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import c_oracle
+        idx = torch.arange(0, total, 104729, device=dev)
+        ref = c_oracle.encode_bf16_bits(src[idx].cpu().view(torch.int16).numpy().view(np.uint16))
+        out["parity_sample_bit_exact"] = bool((q[idx].cpu().numpy() == ref).all())
+    except Exception as e:  # pragma: no cover
+        out["parity_sample_bit_exact"] = f"not checked: {e}"
+    del src, q, h
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sub", action="store_true", help="headline only")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    from _util import dt_code
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_gpus = world
+    peaks = load_peaks()
+    L = _capi()                                    # fails loudly if libfp8_b200.so is missing
+    import fp8_mps_native
+    import fp8_mps_patch
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+
+    # ---------------- headline: C2 GEMV, HBM-resident, graph of ROTATION x PASSES calls
+    M, K, N = C2["M"], C2["K"], C2["N"]
+    x, inv_x = _rand_fp8(torch, (M, K), gen, dev)
+    Ws, inv_ws = [], []
+    for _ in range(ROTATION):
+        w, inv_w = _rand_fp8(torch, (N, K), gen, dev)
+        Ws.append(w)
+        inv_ws.append(inv_w)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    bf16 = dt_code(torch.bfloat16)
+
+    def step():
+        for _ in range(PASSES):
+            for w, s in zip(Ws, inv_ws):
+                _mm(L, torch, x, w, out, bf16, inv_x, s)
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    ms, launches_per_step, t0, t1 = time_graph(torch, step, args.steps, args.warmup, dist)
+    clocks = sampler.summary(t0, t1)
+    ms = max_over_ranks(torch, dist, ms)
+    calls = ROTATION * PASSES
+    ms_per_step = ms / args.steps
+    us_per_call = ms_per_step * 1e3 / calls
+    value = n_gpus * C2_BYTES * calls / (ms_per_step * 1e-3) / 1e9
+    per_gpu = value / n_gpus
+
+    # ---------------- e2e: patched torch._scaled_mm with pinned HOST buffers, copies inside the timed region
+    fp8_mps_patch.install()
+    try:
+        hx = x.cpu().pin_memory()
+        hW = Ws[0].cpu().pin_memory()
+        hout = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
+        dx = torch.empty_like(x)
+        dW = torch.empty_like(Ws[0])
+        sa_d, sb_d = inv_x, inv_ws[0]
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            dW.copy_(hW, non_blocking=True)
+            y = torch._scaled_mm(dx.view(torch.float8_e4m3fn), dW.view(torch.float8_e4m3fn).t(), sa_d, sb_d, None, None,
+                                 torch.bfloat16)
+            hout.copy_(y, non_blocking=True)
+
+        e2e_steps = max(args.steps, 3)
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        n0 = L.fp8b_launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_launches = L.fp8b_launch_count() - n0
+        e2e_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1))
+        e2e_val = n_gpus * C2_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        e2e = {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": int(hx.numel() + hW.numel()),
+               "d2h_bytes_per_step": int(hout.numel() * 2), "ms_per_step": round(e2e_ms / e2e_steps, 4),
+               "steps": e2e_steps, "call": "torch._scaled_mm after fp8_mps_patch.install(); one GEMV per step; "
+               "x and W copied from pinned host memory and the result read back every step",
+               "kernel_launches": int(e2e_launches)}
+    finally:
+        fp8_mps_patch.uninstall()
+
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 _scaled_mm GEMV M=1 K=14336 N=4096, per-tensor scales, bf16 out "
+                               "(BASELINE.json configs[1])",
+                   "step": f"{calls} GEMV calls = {PASSES} passes over {ROTATION} distinct weight matrices, one CUDA graph",
+                   "l2": f"inputs larger than L2: {ROTATION} x 58.7 MB weight rotation (940 MB) per pass",
+                   "algorithmic_bytes_per_call": C2_BYTES, "parallelism": "replicas" if n_gpus > 1 else "single-gpu",
+                   "arith": "e4m3 operands, exact fp16 products, fp32 accumulation (FHFMA)"},
+        "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": round(per_gpu / peaks["hbm"], 4), "traffic": None,
+                     "frac_of_nominal_8000": round(per_gpu / 8000.0, 4), "us_per_launch": round(us_per_call, 3),
+                     "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json)",
+                     "kernel": "fp8_gemv_kernel<1>"},
+        "e2e": e2e,
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clocks,
+    }
+
+    # ---------------- the other BASELINE configs
+    if not args.no_sub:
+        sub = {}
+        try:
+            sub["C1_gemv_M1_K4096_N4096_f16"] = bench_gemv_cfg(torch, L, C1, C1_BYTES, torch.float16, False, gen, dev,
+                                                               peaks, args.steps, args.warmup, rotation=32)
+            sub["C3_gemv_M4_K4096_N4096_bias_bf16"] = bench_gemv_cfg(torch, L, C3, C3_BYTES, torch.bfloat16, True, gen,
+                                                                     dev, peaks, args.steps, args.warmup, rotation=32)
+        except Exception as e:
+            sub["gemv_error"] = repr(e)
+        try:
+            s2 = ClockSampler(torch.cuda.current_device())
+            s2.start()
+            tg0 = time.perf_counter()
+            shard = C4["N"] // n_gpus if n_gpus > 1 else None
+            res, bufs = bench_gemm_c4(torch, L, gen, dev, peaks, args.steps, args.warmup, n_shard=shard)
+            res["clocks"] = s2.summary(tg0, time.perf_counter())
+            s2.stop()
+            key = "C4_gemm_M4096_K3072_N12288_bf16" + (f"_shard{n_gpus}" if n_gpus > 1 else "")
+            sub[key] = res
+            if dist is not None:
+                a, inv_a, w, inv_w, c_local = bufs
+                gathered = torch.empty(n_gpus, C4["M"], shard, dtype=torch.bfloat16, device=dev)
+
+                def sharded_step():
+                    _mm(L, torch, a, w, c_local, bf16, inv_a, inv_w, algo=2)
+                    dist.all_gather_into_tensor(gathered, c_local)
+
+                for _ in range(max(args.warmup, 3)):
+                    sharded_step()
+                torch.cuda.synchronize()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    sharded_step()
+                e1.record()
+                torch.cuda.synchronize()
+                t_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1)) / args.steps
+                comp_us = max_over_ranks(torch, dist, res["us_per_call"])
+                sub[key]["sharded"] = {
+                    "world": n_gpus, "compute_only_us_max_rank": round(comp_us, 2),
+                    "compute_only_tflops_total": round(C4_FLOPS / (comp_us * 1e-6) / 1e12, 1),
+                    "gemm_plus_allgather_us": round(t_ms * 1e3, 2),
+                    "end_to_end_tflops_total": round(C4_FLOPS / (t_ms * 1e-3) / 1e12, 1),
+                    "allgather_recv_bytes_per_gpu": int((n_gpus - 1) * C4["M"] * shard * 2),
+                    "layout": "[world, M, N/world] (rank-major column shards)"}
+            del bufs
+        except Exception as e:
+            sub["gemm_error"] = repr(e)
+        try:
+            if rank == 0:
+                sub["C5_casts_flux_12B"] = bench_casts_c5(torch, L, gen, dev, peaks, args.steps, args.warmup)
+        except Exception as e:
+            sub["cast_error"] = repr(e)
+        line["sub"] = sub
+
+    sampler.stop()
+    if rank == 0 and n_gpus == 1 and not args.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_gemv_baseline()
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,120 @@
+#!/usr/bin/env python3
+"""
+In-tree build of the native code (no JIT cache, so the artefacts travel with the tree):
+
+  libfp8_b200.so                      CUDA kernels + C ABI (include/fp8_b200.h), nvcc, sm_100a only
+  fp8_metal.cpython-*.so              torch extension binding torch tensors to that C ABI
+
+Usage:  python fp8-mps-metal_b200/build.py [--force] [--no-ext]
+
+nvcc cross-compiles for sm_100a without a GPU.  Flags: -gencode arch=compute_100a,code=sm_100a
+-lineinfo (so ncu's source page maps to these files) -O3.
+"""
+
+from __future__ import annotations
+
+import argparse
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libfp8_b200.so")
+
+CU_SOURCES = ["fp8_cast.cu", "fp8_gemv.cu", "fp8_gemm_simt.cu", "fp8_gemm_tcgen05.cu", "fp8_capi.cu"]
+HEADERS = ["fp8_codec.cuh", "fp8_common.cuh", "fp8_mm.cuh"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def ext_path() -> str:
+    return os.path.join(HERE, "fp8_metal" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build command failed:\n  " + " ".join(cmd) + "\n" + r.stdout)
+    return r.stdout
+
+
+def build_lib(force: bool = False) -> str:
+    os.makedirs(OBJ, exist_ok=True)
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(ROOT, "include", "fp8_b200.h")]
+    nvcc = _nvcc()
+    jobs = []
+    objs = []
+    for src in CU_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or not _newer(o, [s] + hdrs):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(_run, jobs))
+    if force or jobs or not _newer(LIB, objs):
+        # extern "C" entry points are exported explicitly; everything else stays hidden
+        _run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                      "-Xcompiler", "-fPIC"])
+    return LIB
+
+
+def build_ext(force: bool = False) -> str:
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    target = ext_path()
+    src = os.path.join(CSRC, "fp8_bridge.cpp")
+    deps = [src, os.path.join(ROOT, "include", "fp8_b200.h"), LIB]
+    if not force and _newer(target, deps):
+        return target
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+           "-DTORCH_EXTENSION_NAME=fp8_metal", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}", "-Wno-attributes"]
+    for i in inc:
+        cmd += ["-isystem", i]
+    cmd += [src, "-o", target, f"-L{HERE}", "-l:libfp8_b200.so", "-Wl,-rpath,$ORIGIN",
+            f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10", "-lc10_cuda", "-ltorch_cuda"]
+    _run(cmd)
+    return target
+
+
+def build_all(force: bool = False, ext: bool = True):
+    out = [build_lib(force)]
+    if ext:
+        out.append(build_ext(force))
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--no-ext", action="store_true")
+    a = ap.parse_args()
+    for p in build_all(a.force, not a.no_ext):
+        print("built", os.path.relpath(p, ROOT))
+    sys.exit(0)

@@ -1,0 +1,214 @@
+// fp8_metal -- the torch extension of the B200 build: a thin binding from torch tensors to the
+// C ABI of libfp8_b200.so (include/fp8_b200.h).
+//
+// It is the analogue of the reference's fp8_bridge.cpp (module `fp8_metal`,
+// fp8_bridge.cpp:361-371) and keeps its three ops with the same names, argument order and
+// TORCH_CHECK behaviour (fp8_bridge.cpp:174-177,191,269):
+//     fp8_scaled_mm(A, B, scale_a, scale_b) -> (M,N) float32
+//     fp8_dequantize(input, scale)          -> float16, same shape
+//     fp8_quantize(input)                   -> (uint8, inv_scale float32[1])
+// Where the reference bridge copies every tensor MPS->CPU->MTLBuffer and blocks on
+// waitUntilCompleted (fp8_bridge.cpp:180-185,244-245), this one passes device pointers and the
+// caller's current CUDA stream and returns without synchronising.  No CUDA kernel lives here and
+// nothing falls back to ATen math: every op is one or two calls into the C ABI.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <tuple>
+
+#include "../../include/fp8_b200.h"
+
+namespace {
+
+int to_fp8b_dtype(at::ScalarType t)
+{
+    switch (t) {
+        case at::kFloat: return FP8B_F32;
+        case at::kHalf: return FP8B_F16;
+        case at::kBFloat16: return FP8B_BF16;
+        default: TORCH_CHECK(false, "fp8_metal: unsupported dtype ", t, " (need float32, float16 or bfloat16)");
+    }
+    return -1;
+}
+
+void check_status(int rc, const char* what)
+{
+    TORCH_CHECK(rc == FP8B_OK, "fp8_metal: ", what, " failed: ", fp8b_status_string(rc),
+                " (status ", rc, ", cuda error ", fp8b_last_cuda_error(), ")");
+}
+
+void* current_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
+
+const uint8_t* u8_ptr(const torch::Tensor& t) { return static_cast<const uint8_t*>(t.data_ptr()); }
+
+torch::Tensor as_device_f32(const torch::Tensor& t, const torch::Device& dev)
+{
+    return t.to(dev, torch::kFloat32).contiguous().reshape({-1});
+}
+
+// ---- fused scaled matmul: everything torch._scaled_mm can ask for, in one kernel -------------
+torch::Tensor fp8_scaled_mm_fused(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
+                                  c10::optional<torch::Tensor> bias, c10::optional<torch::Tensor> scale_result,
+                                  c10::optional<at::ScalarType> out_dtype, int64_t algo,
+                                  c10::optional<torch::Tensor> out)
+{
+    TORCH_CHECK(A.dtype() == torch::kUInt8, "A must be uint8 (FP8 encoded)");
+    TORCH_CHECK(B.dtype() == torch::kUInt8, "B must be uint8 (FP8 encoded)");
+    TORCH_CHECK(A.is_cuda() && B.is_cuda(), "A and B must be CUDA tensors");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2, "A must be (M,K) and B must be (N,K)");
+    TORCH_CHECK(A.is_contiguous(), "A must be contiguous");
+    TORCH_CHECK(B.is_contiguous(), "B must be contiguous");
+    TORCH_CHECK(B.size(1) == A.size(1), "K dimension mismatch between A and B");
+    TORCH_CHECK(A.device() == B.device(), "A and B must be on the same device");
+    const int64_t M = A.size(0), K = A.size(1), N = B.size(0);
+    TORCH_CHECK(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "extent too large");
+
+    c10::cuda::CUDAGuard guard(A.device());
+    torch::Tensor sa = as_device_f32(scale_a, A.device());
+    torch::Tensor sb = as_device_f32(scale_b, A.device());
+    TORCH_CHECK(sa.numel() == 1 || sa.numel() == M, "scale_a must have 1 or M elements");
+    TORCH_CHECK(sb.numel() == 1 || sb.numel() == N, "scale_b must have 1 or N elements");
+
+    const at::ScalarType odt = out_dtype.value_or(at::kFloat);          // out_dtype=None -> fp32 (fp8_mps_patch.py:103)
+    torch::Tensor C;
+    int64_t ldc = N;
+    if (out.has_value()) {
+        C = *out;
+        TORCH_CHECK(C.is_cuda() && C.device() == A.device() && C.dim() == 2 && C.size(0) == M && C.size(1) == N,
+                    "out must be a (M,N) CUDA tensor on A's device");
+        TORCH_CHECK(C.scalar_type() == odt, "out dtype mismatch");
+        TORCH_CHECK(C.stride(1) == 1 && C.stride(0) >= N, "out must be row-major with unit column stride");
+        ldc = C.stride(0);
+    } else {
+        C = torch::empty({M, N}, torch::TensorOptions().dtype(odt).device(A.device()));
+    }
+
+    torch::Tensor bias_t, sr_t;
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = bias->to(A.device()).contiguous().reshape({-1});
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    const float* sr_ptr = nullptr;
+    if (scale_result.has_value() && scale_result->defined()) {
+        sr_t = as_device_f32(*scale_result, A.device());
+        TORCH_CHECK(sr_t.numel() == 1, "scale_result must have 1 element");
+        sr_ptr = sr_t.data_ptr<float>();
+    }
+
+    if (M == 0 || N == 0) return C;
+    int rc = fp8b_scaled_mm(u8_ptr(A), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt), (int)M, (int)N, (int)K, ldc,
+                            sa.data_ptr<float>(), (int)sa.numel(), sb.data_ptr<float>(), (int)sb.numel(),
+                            bias_ptr, bias_dt, sr_ptr, nullptr, 0, (int)algo, current_stream());
+    check_status(rc, "fp8b_scaled_mm");
+    return C;
+}
+
+// ---- the reference bridge's three ops (fp8_bridge.cpp:165, :265, :312) ------------------------
+torch::Tensor fp8_scaled_mm(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b)
+{
+    return fp8_scaled_mm_fused(A, B, scale_a, scale_b, c10::nullopt, c10::nullopt, c10::nullopt, FP8B_MM_AUTO, c10::nullopt);
+}
+
+torch::Tensor fp8_dequantize(torch::Tensor input, torch::Tensor scale)
+{
+    TORCH_CHECK(input.dtype() == torch::kUInt8, "input must be uint8");
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    c10::cuda::CUDAGuard guard(input.device());
+    torch::Tensor in = input.contiguous();
+    torch::Tensor sc = as_device_f32(scale, input.device());
+    TORCH_CHECK(sc.numel() == 1, "scale must be a scalar tensor");
+    torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(torch::kFloat16).device(in.device()));
+    check_status(fp8b_dequant_f16(u8_ptr(in), out.data_ptr(), (size_t)in.numel(), sc.data_ptr<float>(), current_stream()),
+                 "fp8b_dequant_f16");
+    return out;
+}
+
+// FP8 -> dtype exact cast (no scale): the `.to(dtype)` route of the patch in one pass.
+torch::Tensor fp8_dequantize_to(torch::Tensor input, at::ScalarType dtype)
+{
+    TORCH_CHECK(input.dtype() == torch::kUInt8, "input must be uint8");
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    c10::cuda::CUDAGuard guard(input.device());
+    torch::Tensor in = input.contiguous();
+    torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(dtype).device(in.device()));
+    check_status(fp8b_dequant(u8_ptr(in), out.data_ptr(), to_fp8b_dtype(dtype), (size_t)in.numel(), current_stream()),
+                 "fp8b_dequant");
+    return out;
+}
+
+// float -> FP8 without scaling (fp8_mps_native.fp8_encode); reads f32/f16/bf16 natively.
+torch::Tensor fp8_encode(torch::Tensor input)
+{
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    c10::cuda::CUDAGuard guard(input.device());
+    torch::Tensor in = input.contiguous();
+    if (in.scalar_type() != at::kFloat && in.scalar_type() != at::kHalf && in.scalar_type() != at::kBFloat16)
+        in = in.to(torch::kFloat32);                                   // fp8_mps_native.py:142
+    torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(torch::kUInt8).device(in.device()));
+    check_status(fp8b_encode(in.data_ptr(), to_fp8b_dtype(in.scalar_type()), static_cast<uint8_t*>(out.data_ptr()),
+                             (size_t)in.numel(), nullptr, current_stream()),
+                 "fp8b_encode");
+    return out;
+}
+
+std::tuple<torch::Tensor, torch::Tensor> fp8_quantize(torch::Tensor input)
+{
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    c10::cuda::CUDAGuard guard(input.device());
+    torch::Tensor in = input.contiguous();
+    if (in.scalar_type() != at::kFloat && in.scalar_type() != at::kHalf && in.scalar_type() != at::kBFloat16)
+        in = in.to(torch::kFloat32);
+    auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(in.device());
+    torch::Tensor scales = torch::empty({2}, f32);                    // [scale, inv_scale]
+    torch::Tensor scratch = torch::empty({1}, torch::TensorOptions().dtype(torch::kInt32).device(in.device()));
+    torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(torch::kUInt8).device(in.device()));
+    float* sp = scales.data_ptr<float>();
+    const int dt = to_fp8b_dtype(in.scalar_type());
+    check_status(fp8b_amax_scale(in.data_ptr(), dt, (size_t)in.numel(), sp, sp + 1,
+                                 reinterpret_cast<uint32_t*>(scratch.data_ptr()), current_stream()),
+                 "fp8b_amax_scale");
+    check_status(fp8b_encode(in.data_ptr(), dt, static_cast<uint8_t*>(out.data_ptr()), (size_t)in.numel(), sp,
+                             current_stream()),
+                 "fp8b_encode");
+    return std::make_tuple(out, scales.slice(0, 1, 2));
+}
+
+int64_t select_algo(torch::Tensor A, torch::Tensor B, at::ScalarType out_dtype)
+{
+    return fp8b_scaled_mm_select(u8_ptr(A), u8_ptr(B), nullptr, to_fp8b_dtype(out_dtype), (int)A.size(0), (int)B.size(0),
+                                 (int)A.size(1), B.size(0));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    m.doc() = "fp8_metal: B200 (sm_100a) kernels behind the fp8-mps-metal extension API";
+    m.def("fp8_scaled_mm", &fp8_scaled_mm, "FP8 scaled matrix multiplication on the GPU",
+          py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"));
+    m.def("fp8_dequantize", &fp8_dequantize, "FP8 to float16 dequantization on the GPU",
+          py::arg("input"), py::arg("scale"));
+    m.def("fp8_quantize", &fp8_quantize, "Float to FP8 quantization on the GPU", py::arg("input"));
+    m.def("fp8_encode", &fp8_encode, "Float to FP8 encoding without scaling", py::arg("input"));
+    m.def("fp8_dequantize_to", &fp8_dequantize_to, "FP8 to float32/float16/bfloat16 exact cast",
+          py::arg("input"), py::arg("dtype"));
+    m.def("fp8_scaled_mm_fused", &fp8_scaled_mm_fused,
+          "FP8 scaled matmul with fused scales, bias, scale_result and output cast",
+          py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias") = py::none(),
+          py::arg("scale_result") = py::none(), py::arg("out_dtype") = py::none(), py::arg("algo") = 0,
+          py::arg("out") = py::none());
+    m.def("select_algo", &select_algo, py::arg("A"), py::arg("B"), py::arg("out_dtype"));
+    m.def("launch_count", []() { return (uint64_t)fp8b_launch_count(); });
+    m.def("version", []() { return fp8b_version(); });
+    m.attr("ALGO_AUTO") = (int)FP8B_MM_AUTO;
+    m.attr("ALGO_GEMV") = (int)FP8B_MM_GEMV;
+    m.attr("ALGO_TCGEN05") = (int)FP8B_MM_TCGEN05;
+    m.attr("ALGO_SIMT") = (int)FP8B_MM_SIMT;
+}

@@ -1,0 +1,111 @@
+// C-ABI surface of libfp8_b200.so that is not a kernel file's own: library info, device facts, and
+// the scaled-matmul dispatcher (the analogue of the M-based selection in
+// fp8_mps_native.fp8_scaled_mm / fp8_scaled_mm_auto, fp8_mps_native.py:78-93, :193-210).
+#include <mutex>
+#include "fp8_mm.cuh"
+
+namespace fp8b {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local int t_last_cuda_error = 0;
+
+const DeviceInfo& device_info()
+{
+    // One entry per device ordinal, filled on first use (the analogue of the reference bridge's
+    // call_once context, fp8_bridge.cpp:63-71).
+    static DeviceInfo info[64];
+    static std::once_flag once[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        static DeviceInfo bad = {0, 0, 0, 0};
+        return bad;
+    }
+    std::call_once(once[dev], [dev] {
+        DeviceInfo d = {0, 0, 0, 0};
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+        d.ok = (d.cc_major == 10 && d.sm_count > 0) ? 1 : 0;   // the fatbin holds sm_100a code only
+        info[dev] = d;
+    });
+    return info[dev];
+}
+
+static int validate(const MMArgs& a)
+{
+    if (a.M < 0 || a.N < 0 || a.K < 0) return FP8B_ERR_INVALID;
+    if (a.M == 0 || a.N == 0) return FP8B_OK;
+    if (!a.C || !a.sa || !a.sb) return FP8B_ERR_INVALID;
+    if (a.K > 0 && (!a.A || !a.B)) return FP8B_ERR_INVALID;
+    if (!valid_dtype(a.out_dtype)) return FP8B_ERR_INVALID;
+    if (a.bias && !valid_dtype(a.bias_dtype)) return FP8B_ERR_INVALID;
+    if (a.ldc < a.N) return FP8B_ERR_INVALID;
+    if (!(a.sa_len == 1 || a.sa_len == a.M)) return FP8B_ERR_INVALID;
+    if (!(a.sb_len == 1 || a.sb_len == a.N)) return FP8B_ERR_INVALID;
+    return FP8B_OK;
+}
+
+static int select_algo(const MMArgs& a)
+{
+    if (gemv_supported(a)) return FP8B_MM_GEMV;                 // M <= 16, fp8_mps_native.py:208
+    if (tcgen05_supported(a)) return FP8B_MM_TCGEN05;
+    return FP8B_MM_SIMT;
+}
+
+}  // namespace fp8b
+
+using namespace fp8b;
+
+extern "C" int fp8b_version(void) { return FP8B_VERSION; }
+
+extern "C" const char* fp8b_status_string(int status)
+{
+    switch (status) {
+        case FP8B_OK: return "ok";
+        case FP8B_ERR_INVALID: return "invalid argument";
+        case FP8B_ERR_UNSUPPORTED: return "unsupported by the requested entry point (no fallback taken)";
+        case FP8B_ERR_CUDA: return "CUDA call failed (see fp8b_last_cuda_error)";
+        case FP8B_ERR_NO_DEVICE: return "current device is not an sm_100 (B200-class) GPU";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int fp8b_last_cuda_error(void) { return t_last_cuda_error; }
+extern "C" uint64_t fp8b_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" size_t fp8b_scaled_mm_workspace_bytes(int, int, int) { return 0; }   // split-K reduces through DSMEM
+
+extern "C" int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const void* C, int out_dtype,
+                                     int M, int N, int K, int64_t ldc)
+{
+    MMArgs a = {};
+    a.A = A; a.B = B; a.C = const_cast<void*>(C); a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    return select_algo(a);
+}
+
+extern "C" int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out_dtype,
+                              int M, int N, int K, int64_t ldc,
+                              const float* scale_a, int scale_a_len,
+                              const float* scale_b, int scale_b_len,
+                              const void* bias, int bias_dtype,
+                              const float* scale_result,
+                              void* workspace, size_t workspace_bytes,
+                              int algo, void* stream)
+{
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = workspace; a.ws_bytes = workspace_bytes; a.st = (cudaStream_t)stream;
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (M == 0 || N == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (algo == FP8B_MM_AUTO) algo = select_algo(a);
+    switch (algo) {
+        case FP8B_MM_GEMV: return launch_gemv(a);
+        case FP8B_MM_TCGEN05: return launch_gemm_tcgen05(a);
+        case FP8B_MM_SIMT: return launch_gemm_simt(a);
+        default: return FP8B_ERR_INVALID;
+    }
+}

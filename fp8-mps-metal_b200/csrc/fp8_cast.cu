@@ -1,0 +1,422 @@
+// Streaming cast kernels: FP8 -> {f16,bf16,f32} and {f32,f16,bf16} -> FP8, plus the on-device
+// amax -> scale step of fp8_quantize.
+//
+// Reference: fp8_to_half_kernel (fp8_matmul.metal:215-223) and float_to_fp8_kernel (:228-236), one
+// element per thread, with the scale / up-conversion / pre-scale done as separate torch passes
+// on the host side (fp8_mps_native.py:121-122, :142, :170-179).  Here each is ONE pass over HBM:
+// every thread-iteration moves exactly one 16-byte vector on the wide side (the f16/bf16/f32 side)
+// and the matching 4/8-byte vector on the FP8 side, so both sides are fully coalesced
+// (a warp touches 512 contiguous bytes wide-side, 128/256 contiguous bytes FP8-side); UNROLL
+// independent vectors are in flight per thread.  HBM-bound: 3 B/element (16-bit side) or
+// 5 B/element (f32 side) of algorithmic traffic.
+#include "fp8_codec.cuh"
+#include "fp8_common.cuh"
+
+namespace fp8b {
+
+constexpr int kCastThreads = 256;
+constexpr int kCastUnroll = 4;
+
+__device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_v4(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_v2(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u32(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&v));
+    __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);       // exact: e4m3 values fit bf16
+    return *reinterpret_cast<uint32_t*>(&b);
+}
+
+// ------------------------------------------------------------------------------------------
+// FP8 -> wide.  OUT: FP8B_F16 / FP8B_BF16 (8 elements per 16-byte store, 8-byte load) or
+// FP8B_F32 (4 elements per store, 4-byte load).  SCALED (f16 only): fp16 multiply by RN16(scale).
+template <int OUT, bool SCALED>
+__global__ void __launch_bounds__(kCastThreads)
+fp8_to_wide_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
+                   const float* __restrict__ scale)
+{
+    constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;            // elements per 16-byte vector
+    const size_t nvec = n / EPV;
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    uint32_t s2 = 0;
+    if (SCALED) {
+        __half2 s = __float2half2_rn(__ldg(scale));           // RN16(scale), native.py:121
+        s2 = *reinterpret_cast<uint32_t*>(&s);
+    }
+    for (size_t v0 = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v0 < nvec; v0 += stride * kCastUnroll) {
+        if (OUT == FP8B_F32) {
+            uint32_t w[kCastUnroll];
+#pragma unroll
+            for (int u = 0; u < kCastUnroll; ++u) {
+                size_t v = v0 + u * stride;
+                w[u] = v < nvec ? ldg_stream_u32(in + v * 4) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kCastUnroll; ++u) {
+                size_t v = v0 + u * stride;
+                if (v < nvec) {
+                    uint32_t lo, hi;
+                    dec4_f16x2(w[u], lo, hi);
+                    float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
+                    float2 b = __half22float2(*reinterpret_cast<__half2*>(&hi));
+                    uint4 o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y),
+                                         __float_as_uint(b.x), __float_as_uint(b.y));
+                    stg_stream_v4(reinterpret_cast<uint8_t*>(out) + v * 16, o);
+                }
+            }
+        } else {
+            uint2 w[kCastUnroll];
+#pragma unroll
+            for (int u = 0; u < kCastUnroll; ++u) {
+                size_t v = v0 + u * stride;
+                w[u] = v < nvec ? ldg_stream_v2(in + v * 8) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kCastUnroll; ++u) {
+                size_t v = v0 + u * stride;
+                if (v < nvec) {
+                    uint4 o;
+                    dec4_f16x2(w[u].x, o.x, o.y);
+                    dec4_f16x2(w[u].y, o.z, o.w);
+                    if (SCALED) {                               // fp16 multiply, native.py:122
+                        const __half2 s = *reinterpret_cast<const __half2*>(&s2);
+                        uint32_t* p = &o.x;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __half2 r = __hmul2(*reinterpret_cast<__half2*>(&p[j]), s);
+                            p[j] = *reinterpret_cast<uint32_t*>(&r);
+                        }
+                    }
+                    if (OUT == FP8B_BF16) {
+                        o.x = f16x2_to_bf16x2(o.x); o.y = f16x2_to_bf16x2(o.y);
+                        o.z = f16x2_to_bf16x2(o.z); o.w = f16x2_to_bf16x2(o.w);
+                    }
+                    stg_stream_v4(reinterpret_cast<uint8_t*>(out) + v * 16, o);
+                }
+            }
+        }
+    }
+    // tail (< EPV elements): first thread of the grid, scalar
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t i = nvec * EPV; i < n; ++i) {
+            float f = dec1_f32(in[i]);
+            if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
+            else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
+            else {
+                __half h = __float2half_rn(f);
+                if (SCALED) h = __hmul(h, __float2half_rn(__ldg(scale)));
+                reinterpret_cast<__half*>(out)[i] = h;
+            }
+        }
+    }
+}
+
+// Unaligned pointers: same arithmetic, one element per thread-iteration.
+template <int OUT, bool SCALED>
+__global__ void __launch_bounds__(kCastThreads)
+fp8_to_wide_scalar_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
+                          const float* __restrict__ scale)
+{
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    for (size_t i = (size_t)blockIdx.x * kCastThreads + threadIdx.x; i < n; i += stride) {
+        float f = dec1_f32(in[i]);
+        if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
+        else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
+        else {
+            __half h = __float2half_rn(f);
+            if (SCALED) h = __hmul(h, __float2half_rn(__ldg(scale)));
+            reinterpret_cast<__half*>(out)[i] = h;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// wide -> FP8.  IN: f32 (16-byte load = 4 elements, 4-byte store) or f16/bf16 (8 elements, 8-byte
+// store).  PRESCALE: out = enc(f32(in) * prescale[0]) with the multiply in fp32 (native.py:179).
+template <int IN, bool PRESCALE>
+__device__ __forceinline__ void encode_vec(const uint4& w, float s, uint32_t& o0, uint32_t& o1) {
+    if (IN == FP8B_F32) {
+        float a = __uint_as_float(w.x), b = __uint_as_float(w.y), c = __uint_as_float(w.z), d = __uint_as_float(w.w);
+        if (PRESCALE) { a = __fmul_rn(a, s); b = __fmul_rn(b, s); c = __fmul_rn(c, s); d = __fmul_rn(d, s); }
+        o0 = enc4_f32(a, b, c, d);
+        o1 = 0;
+    } else if (PRESCALE) {
+        const uint32_t* p = &w.x;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (IN == FP8B_F16) {
+                float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
+                f[2 * j] = t.x; f[2 * j + 1] = t.y;
+            } else {
+                f[2 * j] = __uint_as_float(p[j] << 16); f[2 * j + 1] = __uint_as_float(p[j] & 0xFFFF0000u);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __fmul_rn(f[j], s);
+        o0 = enc4_f32(f[0], f[1], f[2], f[3]);
+        o1 = enc4_f32(f[4], f[5], f[6], f[7]);
+    } else if (IN == FP8B_F16) {
+        o0 = (uint32_t)enc2_f16x2(w.x) | ((uint32_t)enc2_f16x2(w.y) << 16);
+        o1 = (uint32_t)enc2_f16x2(w.z) | ((uint32_t)enc2_f16x2(w.w) << 16);
+    } else {
+        o0 = (uint32_t)enc2_bf16x2(w.x) | ((uint32_t)enc2_bf16x2(w.y) << 16);
+        o1 = (uint32_t)enc2_bf16x2(w.z) | ((uint32_t)enc2_bf16x2(w.w) << 16);
+    }
+}
+
+template <int IN>
+__device__ __forceinline__ float load_wide_scalar(const void* in, size_t i) {
+    if (IN == FP8B_F32) return reinterpret_cast<const float*>(in)[i];
+    if (IN == FP8B_F16) return __half2float(reinterpret_cast<const __half*>(in)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]);
+}
+
+template <int IN, bool PRESCALE>
+__global__ void __launch_bounds__(kCastThreads)
+wide_to_fp8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_t n,
+                   const float* __restrict__ prescale)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    const size_t nvec = n / EPV;
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    const float s = PRESCALE ? __ldg(prescale) : 1.0f;
+    for (size_t v0 = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v0 < nvec; v0 += stride * kCastUnroll) {
+        uint4 w[kCastUnroll];
+#pragma unroll
+        for (int u = 0; u < kCastUnroll; ++u) {
+            size_t v = v0 + u * stride;
+            w[u] = v < nvec ? ldg_stream_v4(reinterpret_cast<const uint8_t*>(in) + v * 16) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kCastUnroll; ++u) {
+            size_t v = v0 + u * stride;
+            if (v < nvec) {
+                uint32_t o0, o1;
+                encode_vec<IN, PRESCALE>(w[u], s, o0, o1);
+                if (IN == FP8B_F32) stg_stream_u32(out + v * 4, o0);
+                else stg_stream_v2(out + v * 8, make_uint2(o0, o1));
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t i = nvec * EPV; i < n; ++i) {
+            float f = load_wide_scalar<IN>(in, i);
+            if (PRESCALE) f = __fmul_rn(f, s);
+            out[i] = enc1_f32(f);
+        }
+    }
+}
+
+template <int IN, bool PRESCALE>
+__global__ void __launch_bounds__(kCastThreads)
+wide_to_fp8_scalar_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_t n,
+                          const float* __restrict__ prescale)
+{
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    const float s = PRESCALE ? __ldg(prescale) : 1.0f;
+    for (size_t i = (size_t)blockIdx.x * kCastThreads + threadIdx.x; i < n; i += stride) {
+        float f = load_wide_scalar<IN>(in, i);
+        if (PRESCALE) f = __fmul_rn(f, s);
+        out[i] = enc1_f32(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// amax over |f32(in)| -> atomicMax on the float bit pattern (non-negative floats order like
+// unsigned ints; NaN bit patterns sort above inf, so a NaN input yields a NaN amax exactly like
+// torch's abs().max(), fp8_mps_native.py:174).
+template <int IN>
+__global__ void __launch_bounds__(kCastThreads)
+amax_kernel(const void* __restrict__ in, size_t n, uint32_t* __restrict__ amax_bits)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    const size_t nvec = n / EPV;
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    uint32_t m = 0;
+    for (size_t v = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v < nvec; v += stride) {
+        uint4 w = ldg_stream_v4(reinterpret_cast<const uint8_t*>(in) + v * 16);
+        const uint32_t* p = &w.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (IN == FP8B_F32) m = max(m, p[j] & 0x7FFFFFFFu);
+            else if (IN == FP8B_BF16) { m = max(m, (p[j] << 16) & 0x7FFFFFFFu); m = max(m, p[j] & 0x7FFF0000u); }
+            else {
+                float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
+                m = max(m, __float_as_uint(t.x) & 0x7FFFFFFFu);
+                m = max(m, __float_as_uint(t.y) & 0x7FFFFFFFu);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (size_t i = nvec * EPV; i < n; ++i) m = max(m, __float_as_uint(load_wide_scalar<IN>(in, i)) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    __shared__ uint32_t sm[kCastThreads / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < kCastThreads / 32 ? sm[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (threadIdx.x == 0) atomicMax(amax_bits, m);
+    }
+}
+
+template <int IN>
+__global__ void __launch_bounds__(kCastThreads)
+amax_scalar_kernel(const void* __restrict__ in, size_t n, uint32_t* __restrict__ amax_bits)
+{
+    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    uint32_t m = 0;
+    for (size_t i = (size_t)blockIdx.x * kCastThreads + threadIdx.x; i < n; i += stride)
+        m = max(m, __float_as_uint(load_wide_scalar<IN>(in, i)) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(amax_bits, m);
+}
+
+// scale = 448.0/amax in double, as the reference's Python does (fp8_mps_native.py:175-176,:189);
+// resets the scratch word for the next call.
+__global__ void amax_finalize_kernel(uint32_t* amax_bits, float* scale_out, float* inv_scale_out)
+{
+    float amax = __uint_as_float(*amax_bits);
+    double scale = (amax > 0.0f) ? 448.0 / (double)amax : 1.0;
+    if (scale_out) *scale_out = (float)scale;
+    if (inv_scale_out) *inv_scale_out = (float)(1.0 / scale);
+    *amax_bits = 0u;
+}
+
+static int cast_grid(size_t work_items) {
+    const DeviceInfo& di = device_info();
+    size_t want = (work_items + kCastThreads - 1) / kCastThreads;
+    size_t cap = (size_t)di.sm_count * 8;                     // 8 x 256 threads = full occupancy
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace fp8b
+
+using namespace fp8b;
+
+extern "C" int fp8b_dequant_f16(const uint8_t* in, void* out, size_t n, const float* scale, void* stream)
+{
+    if (n == 0) return FP8B_OK;
+    if (!in || !out) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool vec = aligned(in, 8) && aligned(out, 16);
+    if (vec) {
+        int g = cast_grid((n / 8 + kCastUnroll - 1) / kCastUnroll);
+        if (scale) fp8_to_wide_kernel<FP8B_F16, true><<<g, kCastThreads, 0, st>>>(in, out, n, scale);
+        else fp8_to_wide_kernel<FP8B_F16, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
+    } else {
+        int g = cast_grid(n);
+        if (scale) fp8_to_wide_scalar_kernel<FP8B_F16, true><<<g, kCastThreads, 0, st>>>(in, out, n, scale);
+        else fp8_to_wide_scalar_kernel<FP8B_F16, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
+    }
+    return after_launch();
+}
+
+extern "C" int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t n, void* stream)
+{
+    if (!valid_dtype(out_dtype)) return FP8B_ERR_INVALID;
+    if (out_dtype == FP8B_F16) return fp8b_dequant_f16(in, out, n, nullptr, stream);
+    if (n == 0) return FP8B_OK;
+    if (!in || !out) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == FP8B_BF16) {
+        if (aligned(in, 8) && aligned(out, 16))
+            fp8_to_wide_kernel<FP8B_BF16, false><<<cast_grid((n / 8 + kCastUnroll - 1) / kCastUnroll), kCastThreads, 0, st>>>(in, out, n, nullptr);
+        else
+            fp8_to_wide_scalar_kernel<FP8B_BF16, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
+    } else {
+        if (aligned(in, 4) && aligned(out, 16))
+            fp8_to_wide_kernel<FP8B_F32, false><<<cast_grid((n / 4 + kCastUnroll - 1) / kCastUnroll), kCastThreads, 0, st>>>(in, out, n, nullptr);
+        else
+            fp8_to_wide_scalar_kernel<FP8B_F32, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
+    }
+    return after_launch();
+}
+
+template <int IN>
+static int launch_encode(const void* in, uint8_t* out, size_t n, const float* prescale, cudaStream_t st)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    const bool vec = aligned(in, 16) && aligned(out, EPV);
+    if (vec) {
+        int g = cast_grid((n / EPV + kCastUnroll - 1) / kCastUnroll);
+        if (prescale) wide_to_fp8_kernel<IN, true><<<g, kCastThreads, 0, st>>>(in, out, n, prescale);
+        else wide_to_fp8_kernel<IN, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
+    } else {
+        int g = cast_grid(n);
+        if (prescale) wide_to_fp8_scalar_kernel<IN, true><<<g, kCastThreads, 0, st>>>(in, out, n, prescale);
+        else wide_to_fp8_scalar_kernel<IN, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
+    }
+    return after_launch();
+}
+
+extern "C" int fp8b_encode(const void* in, int in_dtype, uint8_t* out, size_t n, const float* prescale, void* stream)
+{
+    if (!valid_dtype(in_dtype)) return FP8B_ERR_INVALID;
+    if (n == 0) return FP8B_OK;
+    if (!in || !out) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == FP8B_F32) return launch_encode<FP8B_F32>(in, out, n, prescale, st);
+    if (in_dtype == FP8B_F16) return launch_encode<FP8B_F16>(in, out, n, prescale, st);
+    return launch_encode<FP8B_BF16>(in, out, n, prescale, st);
+}
+
+template <int IN>
+static int launch_amax(const void* in, size_t n, uint32_t* scratch, cudaStream_t st)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    if (aligned(in, 16)) amax_kernel<IN><<<cast_grid(n / EPV + 1), kCastThreads, 0, st>>>(in, n, scratch);
+    else amax_scalar_kernel<IN><<<cast_grid(n), kCastThreads, 0, st>>>(in, n, scratch);
+    return after_launch();
+}
+
+extern "C" int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* scale_out, float* inv_scale_out,
+                               uint32_t* scratch, void* stream)
+{
+    if (!valid_dtype(in_dtype) || !scratch || (!scale_out && !inv_scale_out)) return FP8B_ERR_INVALID;
+    if (n != 0 && !in) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e);
+    int rc = FP8B_OK;
+    if (n) {
+        if (in_dtype == FP8B_F32) rc = launch_amax<FP8B_F32>(in, n, scratch, st);
+        else if (in_dtype == FP8B_F16) rc = launch_amax<FP8B_F16>(in, n, scratch, st);
+        else rc = launch_amax<FP8B_BF16>(in, n, scratch, st);
+        if (rc != FP8B_OK) return rc;
+    }
+    amax_finalize_kernel<<<1, 1, 0, st>>>(scratch, scale_out, inv_scale_out);
+    return after_launch();
+}

@@ -1,0 +1,31 @@
+// Shared host-side helpers for libfp8_b200 (launch bookkeeping, status plumbing).
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
+#include "../../include/fp8_b200.h"
+
+namespace fp8b {
+
+extern std::atomic<uint64_t> g_launches;       // fp8b_launch_count()
+extern thread_local int t_last_cuda_error;     // fp8b_last_cuda_error()
+
+inline int cuda_fail(cudaError_t e) { t_last_cuda_error = (int)e; return FP8B_ERR_CUDA; }
+
+// Call after every <<<>>> launch: counts it and converts a launch error into a status.
+inline int after_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return cuda_fail(e); }
+    return FP8B_OK;
+}
+
+// One-time device facts (SM count, compute capability) for the current device.
+struct DeviceInfo { int sm_count; int cc_major; int cc_minor; int ok; };
+const DeviceInfo& device_info();
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+inline size_t dtype_size(int dt) { return dt == FP8B_F32 ? 4 : 2; }
+inline bool valid_dtype(int dt) { return dt == FP8B_F32 || dt == FP8B_F16 || dt == FP8B_BF16; }
+
+}  // namespace fp8b

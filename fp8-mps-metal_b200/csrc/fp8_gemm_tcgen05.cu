@@ -1,0 +1,421 @@
+// FP8 GEMM on the 5th-generation tensor cores:  C = epi( A[M,K] * B[N,K]^T ),  both operands
+// K-major e4m3 bytes, fp32 accumulation in tensor memory.
+//
+// Replaces the reference's large-M routes: fp8_scaled_matmul_kernel (fp8_matmul.metal:99-147, one
+// thread per output element, 2K single-byte loads each) and fp8_scaled_mm_fast
+// (fp8_mps_native.py:213-267: two dequantise passes to fp16, two fp16 scale passes, an fp16 GEMM and
+// an fp32 cast -- six launches and 3x the bytes), plus the patch's bias / scale_result / out_dtype
+// passes (fp8_mps_patch.py:95-104).  One launch here.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 128 B A tile and a BN x 128 B
+//               B tile per k-block into a STAGES-deep 128B-swizzled shared-memory ring (mbarrier
+//               complete_tx).  The reference's (N,K) weight layout is already the K-major form
+//               tcgen05 wants, so neither operand is transposed.  TMA zero-fills out-of-range rows and
+//               the K tail; 0x00 decodes to 0, so edges need no special code.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f8f6f4 (M=128, N=BN, K=32),
+//               four per k-block; tcgen05.commit releases each smem slot and finally publishes the
+//               accumulator.
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
+//               *scale_result -> out dtype -> 16-byte global stores.  Two accumulators of BN columns
+//               live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the main loop
+//               of tile i+1.
+// NaN bytes (0x7F/0xFF) make the hardware accumulator NaN where the reference decodes 0
+// (metal:21); the epilogue recomputes exactly those outputs with the masked scalar loop.
+#include <cuda.h>
+#include <mutex>
+#include "fp8_mm.cuh"
+
+namespace fp8b {
+
+constexpr int kBM = 128;          // rows of A per tile = UMMA M
+constexpr int kBK = 128;          // bytes of K per stage = one 128B swizzle span
+constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
+constexpr int kGemmThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kNumEpiWarps = 4;
+
+template <int BN> struct GemmCfg {
+    static constexpr int kABytes = kBM * kBK;
+    static constexpr int kBBytes = BN * kBK;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kTmemCols = 2 * BN;                       // 512 or 256: a power of two >= 32
+    static constexpr int kBarBytes = 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment
+};
+
+struct GemmParams {
+    const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
+    int M, N, K;
+    int num_m_blocks, num_n_blocks, num_k_blocks;
+    Epi epi;
+    int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// Wait with a watchdog: a pipeline bug must surface as a trapped kernel, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3FF) == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 4000000000ull) __trap();      // 4 s
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, e4m3 x e4m3 -> f32
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory operand descriptor (PTX "matrix descriptor", sm_100 version 1):
+//   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups      [46,48) version = 1
+//   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Instruction descriptor for kind::f8f6f4: D = f32 (bits 4-5 = 1), A = B = e4m3 (formats 0),
+// both K-major (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ------------------------------------------------------------------------------ kernel
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                        const __grid_constant__ CUtensorMap tmap_b,
+                        const GemmParams p)
+{
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t gemm_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bar_mem = smem + Cfg::kStages * Cfg::kStageBytes;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bar_mem);
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_mem + 8 * (2 * Cfg::kStages + 4));
+
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps); }
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_idx = (tile % p.num_m_blocks) * kBM;
+                const int n_idx = (tile / p.num_m_blocks) * BN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+                    tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                    tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);           // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK);
+                        const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK);
+                        umma_f8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(empty_bar(stage));                   // smem slot free once these MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                         // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int row_in_tile = q * 32 + lane;
+        const Epi& e = p.epi;
+        const float sr = e.sr ? __ldg(e.sr) : 1.0f;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_idx = (tile % p.num_m_blocks) * kBM;
+            const int n_idx = (tile / p.num_m_blocks) * BN;
+            const int m = m_idx + row_in_tile;
+            const bool m_ok = m < p.M;
+            const float sa = __ldg(e.sa + (size_t)(m_ok ? m : 0) * e.sa_stride);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                __syncwarp();                         // lanes may have diverged on the row/column masks below
+                tmem_ld_x32(t_row + c0, r);
+                tmem_ld_wait();
+                if (c0 + 32 == BN) {                  // last read of this accumulator: hand it back early
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                }
+                const int n0 = n_idx + c0;
+                if (!m_ok || n0 >= p.N) continue;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + j;
+                    float a = __uint_as_float(r[j]);
+                    if (a != a && n < p.N) a = slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)n * p.K, p.K);
+                    const int nn = n < p.N ? n : p.N - 1;
+                    float x = __fmul_rn(a, sa);
+                    x = __fmul_rn(x, __ldg(e.sb + (size_t)nn * e.sb_stride));
+                    if (e.bias) x = __fadd_rn(x, epi_bias(e, nn));
+                    if (e.sr) x = __fmul_rn(x, sr);
+                    v[j] = x;
+                }
+                if (p.vec_store_ok && n0 + 32 <= p.N) {
+                    if (e.out_dtype == FP8B_F32) {
+                        float* dst = reinterpret_cast<float*>(e.C) + (size_t)m * e.ldc + n0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            stg_v4(dst + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]),
+                                   __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+                    } else {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (e.out_dtype == FP8B_BF16) {
+                                __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&b);
+                            } else {
+                                __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
+                        }
+                        uint16_t* dst = reinterpret_cast<uint16_t*>(e.C) + (size_t)m * e.ldc + n0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) stg_v4(dst + 2 * j, pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + j < p.N) epi_store(e, m, n0 + j, v[j]);
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+// rows x K bytes, row-major; box = box_rows x 128 bytes, 128B swizzle.
+static bool encode_operand_map(CUtensorMap* map, const uint8_t* base, int rows, int K, int box_rows)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool tcgen05_supported(const MMArgs& a)
+{
+    // TMA: 16-byte aligned bases and a row pitch (K bytes) that is a multiple of 16.
+    return a.M >= 1 && a.N >= 1 && a.K >= 16 && (a.K % 16 == 0) && aligned(a.A, 16) && aligned(a.B, 16);
+}
+
+template <int BN>
+static int launch_tcgen05_bn(const MMArgs& a)
+{
+    using Cfg = GemmCfg<BN>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(fp8_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err);
+
+    CUtensorMap tmap_a, tmap_b;
+    if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;
+    if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, BN)) return FP8B_ERR_CUDA;
+
+    GemmParams p;
+    p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
+    p.num_m_blocks = (a.M + kBM - 1) / kBM;
+    p.num_n_blocks = (a.N + BN - 1) / BN;
+    p.num_k_blocks = (a.K + kBK - 1) / kBK;
+    p.epi = make_epi(a);
+    const size_t esz = dtype_size(a.out_dtype);
+    p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
+
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    const int sms = device_info().sm_count;
+    const int grid = tiles < sms ? tiles : sms;
+    fp8_gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, a.st>>>(tmap_a, tmap_b, p);
+    return after_launch();
+}
+
+int launch_gemm_tcgen05(const MMArgs& a)
+{
+    if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    // 128x256 tiles when they fill the machine for at least ~2 waves, else 128x128 (finer tail).
+    const int sms = device_info().sm_count;
+    const long tiles256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
+    if (a.N > 128 && tiles256 >= 2L * sms) return launch_tcgen05_bn<256>(a);
+    return launch_tcgen05_bn<128>(a);
+}
+
+}  // namespace fp8b

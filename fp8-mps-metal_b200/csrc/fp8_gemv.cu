@@ -1,0 +1,263 @@
+// FP8 GEMV for M = 1..16:  C[m,n] = epi( sum_k dec(A[m,k]) * dec(B[n,k]) ).
+//
+// Replaces fp8_scaled_vecmat_kernel (fp8_matmul.metal:155-210; one 32-lane simdgroup per output
+// row, 4 bytes per lane per step, exp2() decode, simd_sum) and the M = 2..16 use of
+// fp8_scaled_matmul_kernel (:99-147, dispatch rule fp8_mps_native.py:208).
+//
+// HBM-bound: the weight matrix B (N*K bytes) is streamed exactly once.
+//   * one warp per weight row, 8 rows per CTA; each lane issues UNROLL independent 16-byte
+//     ld.global.nc.L1::no_allocate loads (512 contiguous bytes per warp per load) before
+//     consuming any of them;
+//   * x (the A rows) is decoded once per CTA into shared memory as fp16 (every e4m3 value is
+//     exact in fp16), split in two 16-byte planes so the per-lane LDS.128 are conflict-free;
+//   * weights are decoded in registers with cvt.rn.f16x2.e4m3x2 (2 elements / instruction) and
+//     accumulated with the sm_100 mixed-precision FMA fma.rn.f32.f16 (SASS FHFMA): the fp16 x fp16
+//     product is formed exactly and added into an fp32 accumulator -- the reference's fp32
+//     accumulation (metal:192) without ever widening the operands;
+//   * lanes are reduced with warp shuffles (the simd_sum of metal:202);
+//   * split-K: when N alone cannot fill the GPU the K range is split over a thread-block cluster
+//     (1 x S x 1) and the S partial sums are reduced through distributed shared memory by the
+//     rank-0 CTA, in rank order (deterministic, no workspace, no atomics);
+//   * scales, bias, scale_result and the output cast are fused into the epilogue.
+//   * NaN bytes: the hardware decode yields NaN where the reference decodes 0 (metal:21).  A NaN
+//     accumulator can only come from such a byte, so it is detected after the reduction and that
+//     output alone is recomputed with the masked scalar loop.
+#include <cooperative_groups.h>
+#include "fp8_mm.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace fp8b {
+
+constexpr int kGemvThreads = 256;
+constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kGemvUnroll = 4;
+constexpr int kGemvMaxMT = 4;
+constexpr int kGemvMaxSplit = 8;
+constexpr int kGemvMaxSmem = 96 * 1024;
+
+struct GemvParams {
+    const uint8_t* A;      // already offset to the first row handled by this launch
+    const uint8_t* B;
+    int m0;                // global row index of A row 0 (for scales / output)
+    int N, K;
+    int k_per_split;       // multiple of 16
+    int k_panel;           // multiple of 16; smem holds MT * k_panel fp16
+    Epi epi;
+};
+
+__device__ __forceinline__ uint4 ldg_w_v4(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// acc += w.lo*x.lo + w.hi*x.hi with exact fp16 products and fp32 accumulation (FHFMA).
+__device__ __forceinline__ void fhfma2(float& acc, uint32_t w2, uint32_t x2) {
+    asm("{\n\t.reg .b16 a0, a1, b0, b1;\n\t"
+        "mov.b32 {a0, a1}, %1;\n\tmov.b32 {b0, b1}, %2;\n\t"
+        "fma.rn.f32.f16 %0, a0, b0, %0;\n\tfma.rn.f32.f16 %0, a1, b1, %0;\n\t}"
+        : "+f"(acc) : "r"(w2), "r"(x2));
+}
+
+template <int MT>
+__device__ __forceinline__ void gemv_consume(const uint4& w, const uint4* __restrict__ xs, int nvec_panel, int v,
+                                             float (&acc0)[MT], float (&acc1)[MT])
+{
+    uint32_t w0l, w0h, w1l, w1h, w2l, w2h, w3l, w3h;
+    dec4_f16x2_raw(w.x, w0l, w0h);
+    dec4_f16x2_raw(w.y, w1l, w1h);
+    dec4_f16x2_raw(w.z, w2l, w2h);
+    dec4_f16x2_raw(w.w, w3l, w3h);
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const uint4 xa = xs[(m * 2 + 0) * nvec_panel + v];     // elements 0..7 of the vector
+        const uint4 xb = xs[(m * 2 + 1) * nvec_panel + v];     // elements 8..15
+        fhfma2(acc0[m], w0l, xa.x); fhfma2(acc1[m], w0h, xa.y);
+        fhfma2(acc0[m], w1l, xa.z); fhfma2(acc1[m], w1h, xa.w);
+        fhfma2(acc0[m], w2l, xb.x); fhfma2(acc1[m], w2h, xb.y);
+        fhfma2(acc0[m], w3l, xb.z); fhfma2(acc1[m], w3h, xb.w);
+    }
+}
+
+template <int MT>
+__global__ void __launch_bounds__(kGemvThreads)
+fp8_gemv_kernel(const GemvParams p)
+{
+    extern __shared__ __align__(16) uint8_t gemv_smem[];
+    uint4* xs = reinterpret_cast<uint4*>(gemv_smem);
+    __shared__ float part[kGemvWarps][kGemvMaxMT];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kGemvWarps + warp;
+    const bool row_ok = row < p.N;
+    const int K = p.K;
+    const int k_begin = blockIdx.y * p.k_per_split;
+    const int k_end = min(K, k_begin + p.k_per_split);
+    const uint8_t* wrow = p.B + (size_t)(row_ok ? row : 0) * K;
+
+    float acc0[MT], acc1[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { acc0[m] = 0.0f; acc1[m] = 0.0f; }
+
+    for (int kp = k_begin; kp < k_end; kp += p.k_panel) {
+        const int len = min(k_end - kp, p.k_panel);
+        const int nvec = len >> 4;
+        const int nvec_panel = p.k_panel >> 4;
+        if (kp != k_begin) __syncthreads();
+        // stage x[:, kp : kp+len] as fp16 (raw hardware decode; NaN bytes stay NaN on purpose)
+        for (int i = threadIdx.x; i < MT * nvec; i += kGemvThreads) {
+            const int m = i / nvec, v = i - m * nvec;
+            const uint4 xb = __ldg(reinterpret_cast<const uint4*>(p.A + (size_t)m * K + kp) + v);
+            uint4 lo, hi;
+            dec4_f16x2_raw(xb.x, lo.x, lo.y);
+            dec4_f16x2_raw(xb.y, lo.z, lo.w);
+            dec4_f16x2_raw(xb.z, hi.x, hi.y);
+            dec4_f16x2_raw(xb.w, hi.z, hi.w);
+            xs[(m * 2 + 0) * nvec_panel + v] = lo;
+            xs[(m * 2 + 1) * nvec_panel + v] = hi;
+        }
+        __syncthreads();
+        if (row_ok) {
+            const uint8_t* wp = wrow + kp;
+            int v = lane;
+            for (; v + 32 * (kGemvUnroll - 1) < nvec; v += 32 * kGemvUnroll) {
+                uint4 w[kGemvUnroll];
+#pragma unroll
+                for (int u = 0; u < kGemvUnroll; ++u) w[u] = ldg_w_v4(wp + (size_t)(v + 32 * u) * 16);
+#pragma unroll
+                for (int u = 0; u < kGemvUnroll; ++u) gemv_consume<MT>(w[u], xs, nvec_panel, v + 32 * u, acc0, acc1);
+            }
+            for (; v < nvec; v += 32) {
+                const uint4 w = ldg_w_v4(wp + (size_t)v * 16);
+                gemv_consume<MT>(w, xs, nvec_panel, v, acc0, acc1);
+            }
+        }
+    }
+
+    float s[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        float t = acc0[m] + acc1[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+        s[m] = t;
+    }
+
+    const int S = gridDim.y;
+    if (S == 1) {
+        if (row_ok && lane < MT) {
+            float v = 0.0f;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) if (lane == m) v = s[m];
+            if (v != v) v = slow_dot_masked(p.A + (size_t)lane * K, wrow, K);
+            const int gm = p.m0 + lane;
+            epi_store(p.epi, gm, row, epi_apply(p.epi, v, gm, row));
+        }
+        return;
+    }
+
+    // split-K: reduce the S partial sums through distributed shared memory, in rank order
+    cg::cluster_group cluster = cg::this_cluster();
+    if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) part[warp][m] = s[m];
+    }
+    cluster.sync();
+    if (cluster.block_rank() == 0 && row_ok && lane < MT) {
+        float v = 0.0f;
+        for (int r = 0; r < S; ++r) {
+            const float* rp = cluster.map_shared_rank(&part[0][0], r);
+            v += rp[warp * kGemvMaxMT + lane];
+        }
+        if (v != v) v = slow_dot_masked(p.A + (size_t)lane * K, wrow, K);
+        const int gm = p.m0 + lane;
+        epi_store(p.epi, gm, row, epi_apply(p.epi, v, gm, row));
+    }
+    cluster.sync();
+}
+
+// Any K / any alignment: byte loads, masked scalar decode, fp32 FMA.  Correct, not fast.
+__global__ void __launch_bounds__(kGemvThreads)
+fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kGemvWarps + warp;
+    if (row >= N) return;
+    const uint8_t* wrow = B + (size_t)row * K;
+    for (int m = 0; m < M; ++m) {
+        const uint8_t* x = A + (size_t)m * K;
+        float acc = 0.0f;
+        for (int k = lane; k < K; k += 32) acc = __fmaf_rn(dec1_f32(x[k]), dec1_f32(wrow[k]), acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if (lane == 0) epi_store(epi, m, row, epi_apply(epi, acc, m, row));
+    }
+}
+
+bool gemv_supported(const MMArgs& a) { return a.M >= 1 && a.M <= 16; }
+
+template <int MT>
+static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t st)
+{
+    static bool attr_set = false;                  // benign race: idempotent attribute write
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fp8_gemv_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem);
+        if (e != cudaSuccess) return cuda_fail(e);
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((p.N + kGemvWarps - 1) / kGemvWarps, S, 1);
+    cfg.blockDim = dim3(kGemvThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = S > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemv_kernel<MT>, p);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return after_launch();
+}
+
+int launch_gemv(const MMArgs& a)
+{
+    if (!gemv_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    const Epi epi = make_epi(a);
+    const bool fast = (a.K % 16 == 0) && a.K >= 16 && aligned(a.A, 16) && aligned(a.B, 16);
+    if (!fast) {
+        fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi);
+        return after_launch();
+    }
+    const DeviceInfo& di = device_info();
+    const int row_blocks = (a.N + kGemvWarps - 1) / kGemvWarps;
+    for (int m0 = 0; m0 < a.M; m0 += kGemvMaxMT) {
+        const int mt = a.M - m0 < kGemvMaxMT ? a.M - m0 : kGemvMaxMT;
+        // split K over a cluster until the grid covers the GPU about twice (each CTA keeps >= 2 KB of K)
+        int S = 1;
+        while (S < kGemvMaxSplit && row_blocks * S < 2 * di.sm_count && a.K / (S * 2) >= 2048) S *= 2;
+        int kps = ((a.K + S - 1) / S + 15) & ~15;
+        // shrink S if the rounding left trailing ranks without work
+        while (S > 1 && (size_t)kps * (S - 1) >= (size_t)a.K) { S /= 2; kps = ((a.K + S - 1) / S + 15) & ~15; }
+        int panel = kps;
+        const int max_panel = (kGemvMaxSmem / (2 * mt)) & ~15;
+        if (panel > max_panel) panel = max_panel;
+        GemvParams p;
+        p.A = a.A + (size_t)m0 * a.K; p.B = a.B; p.m0 = m0; p.N = a.N; p.K = a.K;
+        p.k_per_split = kps; p.k_panel = panel; p.epi = epi;
+        const size_t smem = (size_t)mt * panel * 2;
+        int rc;
+        switch (mt) {
+            case 1: rc = launch_gemv_mt<1>(p, S, smem, a.st); break;
+            case 2: rc = launch_gemv_mt<2>(p, S, smem, a.st); break;
+            case 3: rc = launch_gemv_mt<3>(p, S, smem, a.st); break;
+            default: rc = launch_gemv_mt<4>(p, S, smem, a.st); break;
+        }
+        if (rc != FP8B_OK) return rc;
+    }
+    return FP8B_OK;
+}
+
+}  // namespace fp8b

@@ -1,0 +1,154 @@
+/*
+ * fp8_b200.h -- C ABI of libfp8_b200.so: the B200 (sm_100a) implementation of the
+ * fp8-mps-metal FP8 (e4m3fn) hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one kernel-dispatch site of the
+ * reference (audiohacking/fp8-mps-metal); the reference's closest analogue of this ABI is the
+ * buffer-index / setBytes contract of its C++ bridge (fp8_bridge.cpp:209-240) and the
+ * torch.mps.compile_shader call sites in fp8_mps_native.py.
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw DEVICE pointers, extents, dtype enums, a CUDA stream handle (cudaStream_t
+ *     passed as void*; NULL = legacy default stream).  No torch types.
+ *   - no allocation, no host synchronisation, no ownership transfer.  The call enqueues work on
+ *     `stream` and returns.  Re-entrant; thread-safe for distinct streams.
+ *   - optional arguments are NULL pointers (absent), never sentinel values.
+ *   - return value: FP8B_OK (0) or a negative fp8b_status.  There is NO silent fallback: an
+ *     unsupported shape/alignment returns FP8B_ERR_UNSUPPORTED and does nothing; there is no CPU
+ *     path anywhere in this library.
+ *   - the FP8 format is e4m3fn stored as uint8 with the REFERENCE's codec semantics
+ *     (fp8_matmul.metal:19-92): decode maps 0x7F/0xFF to +0.0; encode saturates at +-448 (0x7E),
+ *     flushes |v| < 2^-9 to signed zero (-0.0 -> 0x00), rounds the 3-bit mantissa to nearest-even
+ *     WITHOUT carrying into the exponent.  NaN inputs to encode (undefined in the reference)
+ *     give 0x7F.
+ */
+#ifndef FP8_B200_H
+#define FP8_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FP8B_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define FP8B_API __attribute__((visibility("default")))
+#else
+#define FP8B_API
+#endif
+
+typedef enum fp8b_status {
+    FP8B_OK = 0,
+    FP8B_ERR_INVALID = -1,     /* bad argument (null pointer, negative extent, bad enum, bad scale length) */
+    FP8B_ERR_UNSUPPORTED = -2, /* valid request this entry point cannot serve (alignment, M range, workspace) */
+    FP8B_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see fp8b_last_cuda_error() */
+    FP8B_ERR_NO_DEVICE = -4    /* current device is not compute capability 10.x */
+} fp8b_status;
+
+typedef enum fp8b_dtype {
+    FP8B_F32 = 0,
+    FP8B_F16 = 1,
+    FP8B_BF16 = 2
+} fp8b_dtype;
+
+/* Which matmul kernel fp8b_scaled_mm() picked / should pick. */
+typedef enum fp8b_mm_algo {
+    FP8B_MM_AUTO = 0,    /* M <= 16 -> GEMV; else tcgen05 when its alignment rules hold, else SIMT */
+    FP8B_MM_GEMV = 1,    /* split-K streaming GEMV, M in [1,16]   (replaces fp8_scaled_vecmat_kernel) */
+    FP8B_MM_TCGEN05 = 2, /* tcgen05/TMEM/TMA GEMM                 (replaces fp8_scaled_matmul_kernel / fp8_scaled_mm_fast) */
+    FP8B_MM_SIMT = 3     /* CUDA-core tiled GEMM, any shape/alignment (the no-TMA device path) */
+} fp8b_mm_algo;
+
+/* ---- library / diagnostics ------------------------------------------------------------- */
+
+FP8B_API int fp8b_version(void);
+FP8B_API const char* fp8b_status_string(int status);
+/* cudaError_t of the most recent failing CUDA call on this thread (0 if none). */
+FP8B_API int fp8b_last_cuda_error(void);
+/* Number of kernel launches this library has enqueued since load (all threads).  bench.py
+ * reads it before/after the timed region to report `gpu_launches`. */
+FP8B_API uint64_t fp8b_launch_count(void);
+
+/* ---- casts ------------------------------------------------------------------------------ */
+
+/*
+ * FP8 -> fp16 dequantise.  Replaces fp8_to_half_kernel (fp8_matmul.metal:215-223) together with
+ * the host-side scale pass of fp8_dequantize (fp8_mps_native.py:98-124; bridge fp8_bridge.cpp:265-306):
+ *     out[i] = RN16( half(dec(in[i])) * RN16(scale[0]) )        (fp16 multiply, native.py:121-122)
+ * scale: device pointer to one float, or NULL for the bare kernel (out = half(dec(in))).
+ */
+FP8B_API int fp8b_dequant_f16(const uint8_t* in, void* out_f16, size_t n, const float* scale, void* stream);
+
+/*
+ * FP8 -> {f32,f16,bf16} exact cast (every e4m3 value is representable in all three).  This is
+ * the `.to(dtype)` route of the patch (fp8_mps_patch.py:200-223: dequantise with scale 1, then
+ * .to(dtype)) done in one pass.
+ */
+FP8B_API int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t n, void* stream);
+
+/*
+ * {f32,f16,bf16} -> FP8 encode.  Replaces float_to_fp8_kernel (fp8_matmul.metal:228-236) and the
+ * host-side fp32 up-conversion / pre-scale passes of fp8_encode and fp8_quantize
+ * (fp8_mps_native.py:127-155, :170-187):
+ *     out[i] = enc( f32(in[i]) * prescale[0] )      (fp32 multiply; prescale NULL = no multiply)
+ * The input is read in its native dtype (widening to fp32 is exact, native.py:142).
+ */
+FP8B_API int fp8b_encode(const void* in, int in_dtype, uint8_t* out, size_t n, const float* prescale, void* stream);
+
+/*
+ * amax -> scale, on the device, without the reference's .item() host sync (fp8_mps_native.py:174-176,:189):
+ *     amax      = max_i |f32(in[i])|
+ *     scale_d   = amax > 0 ? 448.0 / (double)amax : 1.0        (Python-double arithmetic)
+ *     scale_out[0]     = (float)scale_d                         (what fp8b_encode takes as prescale)
+ *     inv_scale_out[0] = (float)(1.0 / scale_d)                 (what fp8_quantize returns)
+ * scratch: device pointer to one uint32 the call may clobber (it is reset by the call itself).
+ */
+FP8B_API int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* scale_out, float* inv_scale_out,
+                    uint32_t* scratch, void* stream);
+
+/* ---- scaled matmul ---------------------------------------------------------------------- */
+
+/*
+ * C[m,n] = cast_out( (((sum_k dec(A[m,k]) * dec(B[n,k])) * sa) * sb [+ bias[n]]) [* scale_result[0]] )
+ *
+ * Replaces fp8_scaled_matmul_kernel (fp8_matmul.metal:99-147), fp8_scaled_vecmat_kernel (:155-210),
+ * fp8_scaled_mm_fast (fp8_mps_native.py:213-267) and the patch's separate bias / scale_result / cast
+ * passes (fp8_mps_patch.py:95-104), in one kernel.
+ *
+ *   A            (M,K) uint8 row-major, contiguous (lda = K)
+ *   B            (N,K) uint8 row-major, contiguous -- the reference's "pre-transposed" weight layout
+ *   C            (M,N) out_dtype, row stride ldc elements (ldc >= N); ldc lets a rank write its column
+ *                shard straight into a wider matrix
+ *   scale_a      device float[scale_a_len], scale_a_len in {1, M}   (independently of scale_b: fixes the
+ *   scale_b      device float[scale_b_len], scale_b_len in {1, N}    reference's all-or-nothing scale_mode)
+ *   bias         device [N] of bias_dtype, or NULL
+ *   scale_result device float[1], or NULL
+ *   workspace    device scratch of at least fp8b_scaled_mm_workspace_bytes(M,N,K) bytes (may be NULL
+ *                when that is 0).  Contents are don't-care on entry and exit.
+ *   algo         fp8b_mm_algo; a non-AUTO choice that cannot serve the shape returns
+ *                FP8B_ERR_UNSUPPORTED (no re-dispatch).
+ *
+ * NaN bytes (0x7F/0xFF) in A or B contribute 0, as in the reference (fp8_matmul.metal:21).
+ */
+FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out_dtype,
+                   int M, int N, int K, int64_t ldc,
+                   const float* scale_a, int scale_a_len,
+                   const float* scale_b, int scale_b_len,
+                   const void* bias, int bias_dtype,
+                   const float* scale_result,
+                   void* workspace, size_t workspace_bytes,
+                   int algo, void* stream);
+
+FP8B_API size_t fp8b_scaled_mm_workspace_bytes(int M, int N, int K);
+
+/* The algorithm FP8B_MM_AUTO resolves to for this problem (pointers supply the alignment). */
+FP8B_API int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const void* C, int out_dtype,
+                          int M, int N, int K, int64_t ldc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FP8_B200_H */

@@ -1,0 +1,98 @@
+"""Shared helpers for the tests: ctypes view of the C ABI, torch<->numpy glue."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "fp8-mps-metal_b200")
+LIB_PATH = os.path.join(PKG, "libfp8_b200.so")
+HEADER = os.path.join(ROOT, "include", "fp8_b200.h")
+
+F32, F16, BF16 = 0, 1, 2
+ALGO_AUTO, ALGO_GEMV, ALGO_TCGEN05, ALGO_SIMT = 0, 1, 2, 3
+
+_lib = None
+
+
+def declared_symbols():
+    """Every function include/fp8_b200.h declares (the FP8B_API lines)."""
+    src = open(HEADER).read()
+    return re.findall(r"FP8B_API\s+[\w\s\*]+?\b(fp8b_\w+)\s*\(", src)
+
+
+def capi():
+    """libfp8_b200.so through ctypes, with argument types set."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, i32, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int64
+    L.fp8b_version.restype = i32
+    L.fp8b_status_string.restype = ctypes.c_char_p
+    L.fp8b_status_string.argtypes = [i32]
+    L.fp8b_last_cuda_error.restype = i32
+    L.fp8b_launch_count.restype = ctypes.c_uint64
+    L.fp8b_dequant_f16.restype = i32
+    L.fp8b_dequant_f16.argtypes = [vp, vp, sz, vp, vp]
+    L.fp8b_dequant.restype = i32
+    L.fp8b_dequant.argtypes = [vp, vp, i32, sz, vp]
+    L.fp8b_encode.restype = i32
+    L.fp8b_encode.argtypes = [vp, i32, vp, sz, vp, vp]
+    L.fp8b_amax_scale.restype = i32
+    L.fp8b_amax_scale.argtypes = [vp, i32, sz, vp, vp, vp, vp]
+    L.fp8b_scaled_mm.restype = i32
+    L.fp8b_scaled_mm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp, vp, sz, i32, vp]
+    L.fp8b_scaled_mm_workspace_bytes.restype = sz
+    L.fp8b_scaled_mm_workspace_bytes.argtypes = [i32, i32, i32]
+    L.fp8b_scaled_mm_select.restype = i32
+    L.fp8b_scaled_mm_select.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64]
+    _lib = L
+    return L
+
+
+def dt_code(torch_dtype):
+    import torch
+    return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[torch_dtype]
+
+
+def dt_name(torch_dtype):
+    import torch
+    return {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16", None: "f32"}[torch_dtype]
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def p(t):
+    """device pointer of a torch tensor (or None)."""
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def mm_capi(A, B, sa, sb, bias=None, sr=None, out_dtype=None, algo=ALGO_AUTO, out=None):
+    """fp8b_scaled_mm through the raw C ABI on torch CUDA tensors."""
+    import torch
+    L = capi()
+    M, K = A.shape
+    N = B.shape[0]
+    odt = out_dtype or torch.float32
+    C = out if out is not None else torch.empty(M, N, dtype=odt, device=A.device)
+    ldc = C.stride(0) if C.dim() == 2 and M > 0 else N
+    sa = sa.to(device=A.device, dtype=torch.float32).contiguous().reshape(-1)
+    sb = sb.to(device=A.device, dtype=torch.float32).contiguous().reshape(-1)
+    rc = L.fp8b_scaled_mm(p(A), p(B), p(C), dt_code(odt), M, N, K, ldc, p(sa), sa.numel(), p(sb), sb.numel(),
+                          p(bias), dt_code(bias.dtype) if bias is not None else 0, p(sr), None, 0, algo, stream_ptr())
+    return rc, C
+
+
+def to_np(t):
+    """torch tensor (any float dtype, any device) -> float32 numpy, exactly."""
+    return t.detach().float().cpu().numpy()
+
+
+def u8_np(t):
+    import torch
+    return t.detach().view(torch.uint8).cpu().numpy()

@@ -1,0 +1,202 @@
+"""GPU parity: the streaming cast kernels vs the oracle / the reference-generated fixtures.
+Bit-exact everywhere (integer/byte work).  Calls go through the raw C ABI (ctypes) and through
+the reference-shaped Python API (fp8_mps_native)."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle
+import fp8_oracle as o
+from _util import BF16, F16, F32, capi, dt_code, p, stream_ptr, to_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAN_SENTINEL = 0xFF
+
+
+def _encode_capi(x, prescale=None):
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    rc = capi().fp8b_encode(p(x), dt_code(x.dtype), p(out), x.numel(), p(prescale), stream_ptr())
+    assert rc == 0, capi().fp8b_status_string(rc)
+    return out
+
+
+def _dequant_capi(u8, dtype, scale=None):
+    out = torch.empty(u8.shape, dtype=dtype, device=u8.device)
+    if scale is not None or dtype == torch.float16:
+        assert dtype == torch.float16
+        rc = capi().fp8b_dequant_f16(p(u8), p(out), u8.numel(), p(scale), stream_ptr())
+    else:
+        rc = capi().fp8b_dequant(p(u8), p(out), dt_code(dtype), u8.numel(), stream_ptr())
+    assert rc == 0, capi().fp8b_status_string(rc)
+    return out
+
+
+# ------------------------------------------------------------------ decode
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_decode_all_256_patterns(golden, dtype):
+    """test_fp8_metal.py:53-94 (gate 0.5 abs; README claims 0.0): here bit-exact incl. NaN->0, 0x80->-0."""
+    ref = golden["codec"]["decode_table"]
+    b = torch.arange(256, dtype=torch.int32).to(torch.uint8).to(DEV)
+    out = _dequant_capi(b, dtype)
+    got = to_np(out)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # repeat so the vector path (not just the scalar tail) sees every pattern at every lane position
+    rep = b.repeat(257)[3:]                      # misaligned start -> scalar kernel
+    got2 = to_np(_dequant_capi(rep, dtype))
+    assert np.array_equal(got2.view(np.uint32), np.tile(ref, 257)[3:].view(np.uint32))
+    rep = b.repeat(64)                           # aligned -> vector kernel
+    got3 = to_np(_dequant_capi(rep, dtype))
+    assert np.array_equal(got3.view(np.uint32), np.tile(ref, 64).view(np.uint32))
+
+
+def test_dequantize_scaled_golden(golden):
+    """fp8_dequantize = fp16 multiply by half(scale) (fp8_mps_native.py:121-122), fixture from torch CPU."""
+    import fp8_mps_native
+    h = golden["host"]
+    b = torch.arange(256, dtype=torch.int32).to(torch.uint8).to(DEV).repeat(16)
+    for i, s in enumerate(h["deq_scales"]):
+        sc = torch.tensor([float(s)], dtype=torch.float32, device=DEV)
+        want = np.tile(h["deq_out"][i], 16)
+        got = _dequant_capi(b, torch.float16, sc).view(torch.int16).cpu().numpy().view(np.uint16)
+        assert np.array_equal(got, want), f"scale {s}"
+        got2 = fp8_mps_native.fp8_dequantize(b, sc)
+        assert got2.dtype == torch.float16 and got2.shape == b.shape
+        assert np.array_equal(got2.view(torch.int16).cpu().numpy().view(np.uint16), want)
+        got3 = fp8_mps_native.fp8_dequantize(b[5:261].cpu(), torch.tensor(float(s)))   # CPU in, odd offset
+        assert got3.device.type == "cuda"
+        assert np.array_equal(got3.view(torch.int16).cpu().numpy().view(np.uint16), want[5:261])
+
+
+# ------------------------------------------------------------------ encode
+
+def _check_encode(got_u8, ref_u8):
+    got = got_u8.cpu().numpy().reshape(-1)
+    ok = ref_u8 != NAN_SENTINEL
+    bad = np.nonzero(got[ok] != ref_u8[ok])[0]
+    assert bad.size == 0, f"{bad.size} mismatches, first at {bad[:5]}"
+    assert np.all(got[~ok] == 0x7F)              # NaN inputs: build-defined 0x7F
+
+
+def test_encode_all_bf16_patterns(golden):
+    bits = torch.arange(65536, dtype=torch.int32).to(torch.int16).to(DEV)
+    x = bits.view(torch.bfloat16)
+    _check_encode(_encode_capi(x), golden["codec"]["enc_bf16_all"])
+    _check_encode(_encode_capi(x.float()), golden["codec"]["enc_bf16_all"])          # same values via fp32 path
+    _check_encode(_encode_capi(x[1:]), golden["codec"]["enc_bf16_all"][1:])          # unaligned -> scalar kernel
+    one = torch.ones(1, dtype=torch.float32, device=DEV)
+    _check_encode(_encode_capi(x, one), golden["codec"]["enc_bf16_all"])             # prescale path, * 1.0
+
+
+def test_encode_all_fp16_patterns(golden):
+    bits = torch.arange(65536, dtype=torch.int32).to(torch.int16).to(DEV)
+    x = bits.view(torch.float16)
+    _check_encode(_encode_capi(x), golden["codec"]["enc_fp16_all"])
+    _check_encode(_encode_capi(x.float()), golden["codec"]["enc_fp16_all"])
+    _check_encode(_encode_capi(x[3:]), golden["codec"]["enc_fp16_all"][3:])
+
+
+def test_encode_fp32_golden(golden):
+    x = torch.from_numpy(golden["codec"]["enc_f32_in"]).to(DEV)
+    _check_encode(_encode_capi(x), golden["codec"]["enc_f32_out"])
+    _check_encode(_encode_capi(x[1:]), golden["codec"]["enc_f32_out"][1:])
+
+
+def test_known_answers_and_api(golden):
+    import fp8_mps_native
+    kat = golden["kat"]
+    vals = torch.tensor([v for v, _ in kat["encode"]], dtype=torch.float32)
+    got = fp8_mps_native.fp8_encode(vals)                       # CPU input is moved (native.py:142)
+    assert got.device.type == "cuda" and got.dtype == torch.uint8
+    assert got.cpu().tolist() == [b for _, b in kat["encode"]]
+    t = torch.tensor(kat["torch_cpu_equal"], dtype=torch.float32, device=DEV)
+    assert fp8_mps_native.fp8_encode(t).cpu().tolist() == kat["torch_cpu_bytes"]     # test_mps_vs_cpu.py:303
+    assert fp8_mps_native.fp8_encode(torch.empty(0, device=DEV)).numel() == 0
+    assert fp8_mps_native.fp8_encode(torch.zeros(3, 5, 7, device=DEV)).shape == (3, 5, 7)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 31, 257, 4099, 1 << 20, (1 << 22) + 13])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_encode_decode_random_sizes(n, dtype):
+    """Ragged sizes: vector body + scalar tail, against the C oracle."""
+    g = torch.Generator().manual_seed(n)
+    scale = [1.0, 0.02, 100.0][n % 3]
+    x = (torch.randn(n, generator=g) * scale).to(dtype)
+    xd = x.to(DEV)
+    got = _encode_capi(xd).cpu().numpy()
+    if dtype == torch.bfloat16:
+        ref = c_oracle.encode_bf16_bits(x.view(torch.int16).numpy().view(np.uint16))
+    else:
+        ref = c_oracle.encode(x.numpy())
+    assert np.array_equal(got, ref)
+    for odt in (torch.float16, torch.bfloat16, torch.float32):
+        back = to_np(_dequant_capi(torch.from_numpy(ref).to(DEV), odt))
+        assert np.array_equal(back.view(np.uint32), o.decode(ref).view(np.uint32))
+
+
+def test_quantize_golden_and_random(golden):
+    """fp8_quantize: device-side amax -> double-precision scale -> fused multiply+encode
+    must equal the reference's host arithmetic (fp8_mps_native.py:174-189) bit for bit."""
+    import fp8_mps_native
+    h = golden["host"]
+    for i in range(int(h["n_quant"])):
+        x = torch.from_numpy(h[f"q{i}_in"]).to(DEV)
+        q, inv = fp8_mps_native.fp8_quantize(x)
+        assert q.dtype == torch.uint8 and inv.dtype == torch.float32 and inv.shape == (1,)
+        assert np.array_equal(q.cpu().numpy(), h[f"q{i}_bytes"]), i
+        assert np.array_equal(inv.cpu().numpy().view(np.uint32), h[f"q{i}_inv"].view(np.uint32)), i
+    g = torch.Generator().manual_seed(5)
+    for n, s in [(1000003, 1.0), (4096 * 4096, 0.02), (77, 300.0)]:
+        x = torch.randn(n, generator=g) * s
+        q, inv = fp8_mps_native.fp8_quantize(x)
+        rq, rinv = o.fp8_quantize(x.numpy())
+        assert np.array_equal(q.cpu().numpy(), rq)
+        assert np.array_equal(inv.cpu().numpy().view(np.uint32), rinv.view(np.uint32))
+    # bf16 / fp16 inputs are widened exactly (native.py:170)
+    xb = (torch.randn(50000, generator=g) * 3).to(torch.bfloat16)
+    q, inv = fp8_mps_native.fp8_quantize(xb.to(DEV))
+    rq, rinv = o.fp8_quantize(xb.float().numpy())
+    assert np.array_equal(q.cpu().numpy(), rq) and np.array_equal(inv.cpu().numpy().view(np.uint32), rinv.view(np.uint32))
+    # roundtrip gate of the reference (test_fp8_metal.py:167-188)
+    x = torch.tensor([0.0, 1.0, -1.0, 0.5, -0.5, 100.0, -100.0, 448.0])
+    q, sc = fp8_mps_native.fp8_quantize(x)
+    d = fp8_mps_native.fp8_dequantize(q, sc)
+    assert (d.cpu().float() - x).abs().max().item() < 50.0
+
+
+def test_full_size_properties():
+    """BASELINE config 5 scale (one FLUX linear, 21504x3072 = 66 M elements, and a 1 Gi-element sweep
+    of raw bytes): size-independent properties instead of an element-wise CPU oracle."""
+    n = 21504 * 3072
+    g = torch.Generator(device=DEV).manual_seed(11)
+    w = (torch.randn(n, generator=g, device=DEV) * 0.02).to(torch.bfloat16)
+    q = _encode_capi(w)
+    # (1) idempotence: enc(dec(enc(x))) == enc(x)
+    d = _dequant_capi(q, torch.bfloat16)
+    q2 = _encode_capi(d)
+    assert torch.equal(q, q2)
+    # (2) the encoder never emits a NaN code and never emits -0 for an input that is not negative
+    assert int(((q & 0x7F) == 0x7F).sum()) == 0
+    assert int(((q == 0x80) & (w >= 0)).sum()) == 0
+    # (3) |dec(enc(x)) - x| <= half a grid step (relative 1/16) or the flush threshold
+    err = (d.float() - w.float()).abs()
+    bound = torch.maximum(w.float().abs() / 16.0, torch.full_like(err, 2.0 ** -9))
+    assert bool((err <= bound).all())
+    # (4) a strided 1 M sample equals the C oracle bit for bit
+    idx = torch.arange(0, n, 61, device=DEV)
+    sample = w[idx].cpu()
+    ref = c_oracle.encode_bf16_bits(sample.view(torch.int16).numpy().view(np.uint16))
+    assert np.array_equal(q[idx].cpu().numpy(), ref)
+    # (5) byte histogram of the full result equals the histogram implied by the sample's law:
+    #     checksum of checksums -- sum over 64 Ki-element blocks of the byte sums, GPU vs itself
+    #     re-encoded from fp32 input (a different kernel instantiation must agree exactly)
+    q3 = _encode_capi(w.float())
+    assert torch.equal(q, q3)
+    del w, d, q2, q3, err, bound
+    # raw-byte sweep: dec -> enc is the identity except {0x7F,0xFF,0x80} -> 0x00
+    b = torch.randint(0, 256, (1 << 30,), dtype=torch.uint8, device=DEV, generator=g)
+    h = _dequant_capi(b, torch.float16)
+    rb = _encode_capi(h)
+    expect = torch.where(((b & 0x7F) == 0x7F) | (b == 0x80), torch.zeros_like(b), b)
+    assert torch.equal(rb, expect)

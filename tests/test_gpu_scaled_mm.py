@@ -1,0 +1,267 @@
+"""GPU parity: `_scaled_mm` (GEMV, tcgen05 GEMM, SIMT GEMM) vs the fp32 dequantise-then-matmul oracle.
+
+Tolerances (relative RMSE against oracle/fp8_oracle.scaled_mm on identical bytes, fp64-summed):
+    fp32 out  <= 5e-6  for the CUDA-core kernels (exact products, fp32 accumulation; only the summation
+                       order differs from the oracle)
+              <= 1e-4  for the tensor-core kernel (accumulation precision of tcgen05 kind::f8f6f4 is
+                       whatever the hardware does; measured and printed by test_tcgen05_accumulation_precision)
+    fp16 out  <= 5e-4  (output rounding floor 2.1e-4)
+    bf16 out  <= 3e-3  (output rounding floor 1.7e-3)
+plus max-abs <= 2 ulp of the output dtype at the oracle's RMS magnitude scale.
+The reference's own gates are far looser: rel-RMSE < 15 % against the UN-quantised fp32 product
+(test_fp8_metal.py:122,161,215) and 1e-4 abs between its two dispatchers on tiny shapes
+(test_cross_validation.py:187)."""
+import numpy as np
+import pytest
+import torch
+
+import fp8_oracle as o
+from _util import ALGO_AUTO, ALGO_GEMV, ALGO_SIMT, ALGO_TCGEN05, capi, dt_name, mm_capi, to_np
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+TOL = {"f32": 5e-6, "f16": 5e-4, "bf16": 3e-3}
+ULP = {"f32": 2.0 ** -23, "f16": 2.0 ** -10, "bf16": 2.0 ** -7}
+
+
+def _rand_fp8(shape, seed, kind="bytes"):
+    rng = np.random.default_rng(seed)
+    if kind == "bytes":                                   # every byte value, NaN codes excluded
+        b = rng.integers(0, 256, shape, dtype=np.uint8)
+        b[(b & 0x7F) == 0x7F] = 0x3C
+        return b
+    x = rng.standard_normal(shape).astype(np.float32)     # "randn -> quantise" like the reference tests
+    q, inv = o.fp8_quantize(x)
+    return q, inv
+
+
+def _check(got_t, ref, out_dtype, tol=None, what=""):
+    name = dt_name(out_dtype)
+    got = to_np(got_t)
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all(), what
+    e = o.rel_rmse(got, ref)
+    rms = float(np.sqrt(np.mean(ref.astype(np.float64) ** 2)))
+    mx = float(np.abs(got.astype(np.float64) - ref).max())
+    tol = TOL[name] if tol is None else tol
+    assert e <= tol, f"{what}: rel-RMSE {e:.3e} > {tol:.1e}"
+    # max-abs: 2 ulp of the out dtype at the larger of the RMS and the element magnitude
+    scale = np.maximum(np.abs(ref), rms)
+    lim = 2 * ULP[name] * scale + (tol * 40) * rms
+    assert (np.abs(got.astype(np.float64) - ref) <= lim).all(), f"{what}: max-abs {mx:.3e}"
+    return e
+
+
+def _run_case(M, K, N, out_dtype, algo, seed, per_row_a=False, per_row_b=False, bias_dtype=None,
+              scale_result=False, kind="bytes", tol=None):
+    A = _rand_fp8((M, K), seed, "bytes")
+    B = _rand_fp8((N, K), seed + 1, "bytes")
+    rng = np.random.default_rng(seed + 2)
+    sa = (rng.random(M if per_row_a else 1).astype(np.float32) + 0.5) * 0.01
+    sb = (rng.random(N if per_row_b else 1).astype(np.float32) + 0.5) * 0.02
+    bias = rng.standard_normal(N).astype(np.float32) if bias_dtype is not None else None
+    sr = np.array([0.75], dtype=np.float32) if scale_result else None
+    tA, tB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+    tbias = None
+    if bias is not None:
+        tbias = torch.from_numpy(bias).to(DEV).to(bias_dtype)
+        bias = to_np(tbias)                               # what the kernel actually sees
+    tsr = torch.from_numpy(sr).to(DEV) if sr is not None else None
+    rc, C = mm_capi(tA, tB, torch.from_numpy(sa), torch.from_numpy(sb), tbias, tsr, out_dtype, algo)
+    assert rc == 0, capi().fp8b_status_string(rc)
+    ref = o.scaled_mm(A, B, sa, sb, bias, sr, dt_name(out_dtype))
+    return _check(C, ref, out_dtype, tol, f"M{M} K{K} N{N} {dt_name(out_dtype)} algo{algo}")
+
+
+# ------------------------------------------------------------------ GEMV (M <= 16)
+
+@pytest.mark.parametrize("M,K,N,odt,kw", [
+    (1, 512, 256, None, {}),                                   # test_fp8_metal.py:191-218
+    (1, 4096, 4096, torch.float16, {}),                        # BASELINE config 1
+    (1, 14336, 4096, torch.bfloat16, {}),                      # BASELINE config 2
+    (4, 4096, 4096, torch.bfloat16, {"bias_dtype": torch.bfloat16}),   # BASELINE config 3
+    (1, 4096, 64, None, {}),                                   # small N -> cluster split-K
+    (2, 8192, 40, None, {"per_row_b": True}),                  # split-K, ragged N
+    (3, 4112, 1001, torch.float16, {"per_row_a": True, "per_row_b": True, "bias_dtype": torch.float32}),
+    (5, 1024, 333, None, {"scale_result": True}),              # M > 4: two passes
+    (16, 2048, 512, torch.bfloat16, {"per_row_a": True}),
+    (1, 16, 8, None, {}),                                      # minimum aligned K
+    (1, 100000, 24, None, {}),                                 # K panel loop (x does not fit one smem panel) + split
+    (4, 65536, 16, None, {}),
+    (2, 37, 5, None, {}),                                      # K % 16 != 0 -> generic kernel
+    (1, 3, 2, None, {}),
+    (7, 130, 33, torch.float16, {"bias_dtype": torch.float16}),
+])
+def test_gemv(M, K, N, odt, kw):
+    _run_case(M, K, N, odt, ALGO_AUTO, seed=M * 7 + K + N, **kw)
+    if odt is None:
+        _run_case(M, K, N, odt, ALGO_GEMV, seed=K, kind="bytes", **kw)
+
+
+def test_gemv_matches_reference_summation_to_fp32_noise():
+    """Against the plain-C restatement of the shader's own loop order (oracle/fp8_oracle.c):
+    same fp32 products, different summation order only."""
+    import c_oracle
+    A = _rand_fp8((1, 4096), 1)
+    B = _rand_fp8((512, 4096), 2)
+    sa = np.array([0.01], np.float32)
+    sb = np.array([0.03], np.float32)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa), torch.from_numpy(sb))
+    assert rc == 0
+    assert o.rel_rmse(to_np(C), c_oracle.scaled_mm(A, B, sa, sb)) < 2e-6
+
+
+def test_gemv_nan_bytes_decode_to_zero():
+    """fp8_matmul.metal:21 -- 0x7F / 0xFF contribute 0; the fast path repairs NaN accumulators."""
+    rng = np.random.default_rng(0)
+    A = rng.integers(0, 256, (2, 2048), dtype=np.uint8)       # NaN codes left in
+    B = rng.integers(0, 256, (96, 2048), dtype=np.uint8)
+    B[5, 100] = 0x7F
+    B[17, 7] = 0xFF
+    A[1, 33] = 0x7F
+    sa = np.array([1.0], np.float32)
+    sb = np.array([1.0], np.float32)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa), torch.from_numpy(sb))
+    assert rc == 0
+    _check(C, o.scaled_mm(A, B, sa, sb), None, what="nan bytes")
+
+
+def test_gemv_rejects_large_m_when_forced():
+    A = torch.zeros(17, 64, dtype=torch.uint8, device=DEV)
+    B = torch.zeros(8, 64, dtype=torch.uint8, device=DEV)
+    rc, _ = mm_capi(A, B, torch.ones(1), torch.ones(1), algo=ALGO_GEMV)
+    assert rc == -2                                           # FP8B_ERR_UNSUPPORTED, no silent re-dispatch
+
+
+# ------------------------------------------------------------------ tensor-core GEMM
+
+def test_tcgen05_accumulation_precision():
+    """Measures (and bounds) how far tcgen05 kind::f8f6f4 accumulation is from exact fp32."""
+    res = {}
+    for K in (128, 1024, 4096, 16384):
+        res[K] = _run_case(256, K, 256, None, ALGO_TCGEN05, seed=K, tol=1e-4)
+    print("tcgen05 fp32-out rel-RMSE vs exact:", {k: f"{v:.2e}" for k, v in res.items()})
+
+
+@pytest.mark.parametrize("M,K,N,odt,kw", [
+    (128, 128, 128, None, {}),
+    (64, 256, 128, None, {}),                                 # test_fp8_metal.py:97-164 shape
+    (32, 64, 48, None, {}),                                   # test_cross_validation.py:166-198 shape
+    (17, 64, 40, torch.float16, {"bias_dtype": torch.float16}),
+    (256, 512, 384, torch.bfloat16, {"per_row_a": True, "per_row_b": True}),
+    (200, 336, 1000, torch.bfloat16, {"bias_dtype": torch.bfloat16, "scale_result": True}),   # ragged everything
+    (129, 2064, 257, None, {"per_row_b": True}),
+    (1000, 1024, 3000, torch.float16, {}),                    # multi-tile, both tile widths
+    (2048, 3072, 4096, torch.bfloat16, {"bias_dtype": torch.float32}),   # 128x256 tiles, > 2 waves
+    (4, 4096, 512, None, {}),                                 # small M forced onto tensor cores
+])
+def test_tcgen05_gemm(M, K, N, odt, kw):
+    tol = 1e-4 if odt is None else None
+    _run_case(M, K, N, odt, ALGO_TCGEN05, seed=M + K + N, tol=tol, **kw)
+
+
+@pytest.mark.parametrize("M,K,N,odt,kw", [
+    (33, 37, 65, None, {}),
+    (64, 256, 128, torch.bfloat16, {"bias_dtype": torch.bfloat16}),
+    (130, 1000, 70, torch.float16, {"per_row_a": True, "per_row_b": True, "scale_result": True}),
+])
+def test_simt_gemm(M, K, N, odt, kw):
+    _run_case(M, K, N, odt, ALGO_SIMT, seed=M * K + N, **kw)
+
+
+def test_auto_dispatch_rules():
+    L = capi()
+    A = torch.zeros(64, 256, dtype=torch.uint8, device=DEV)
+    B = torch.zeros(128, 256, dtype=torch.uint8, device=DEV)
+    sel = lambda a, b: L.fp8b_scaled_mm_select(a.data_ptr(), b.data_ptr(), None, 0, a.shape[0], b.shape[0], a.shape[1], b.shape[0])
+    assert sel(A[:16], B) == ALGO_GEMV                        # M <= 16 (fp8_mps_native.py:208)
+    assert sel(A, B) == ALGO_TCGEN05
+    A2 = torch.zeros(64, 250, dtype=torch.uint8, device=DEV)
+    B2 = torch.zeros(128, 250, dtype=torch.uint8, device=DEV)
+    assert sel(A2, B2) == ALGO_SIMT                           # K % 16 != 0: TMA cannot describe it
+    rc, _ = mm_capi(A2, B2, torch.ones(1), torch.ones(1), algo=ALGO_TCGEN05)
+    assert rc == -2
+    _run_case(40, 250, 72, None, ALGO_AUTO, seed=9)           # ... and AUTO still computes it on the GPU
+
+
+def test_tcgen05_nan_bytes_and_strided_output():
+    rng = np.random.default_rng(4)
+    M, K, N = 160, 512, 320
+    A = rng.integers(0, 256, (M, K), dtype=np.uint8)
+    B = rng.integers(0, 256, (N, K), dtype=np.uint8)          # ~0.8 % NaN codes
+    sa = np.array([0.02], np.float32)
+    sb = np.array([0.01], np.float32)
+    wide = torch.full((M, 2 * N + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    out = wide[:, 8:8 + N]                                    # column shard of a wider matrix (ldc > N)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa),
+                    torch.from_numpy(sb), out_dtype=torch.bfloat16, algo=ALGO_TCGEN05, out=out)
+    assert rc == 0
+    _check(out, o.scaled_mm(A, B, sa, sb, out_dtype="bf16"), torch.bfloat16, what="nan+strided")
+    assert bool((wide[:, :8] == 7.0).all()) and bool((wide[:, 8 + N:] == 7.0).all())   # nothing outside the shard
+
+
+def test_flux_linear_full_size_against_oracle_and_simt():
+    """BASELINE config 4 at full size: M=4096 K=3072 N=12288, per-tensor scales, bf16 out.
+    Oracle: numpy fp32 BLAS dequantise-then-matmul on a 512-row slab (exact fp64 on a corner),
+    plus the independent CUDA-core kernel on the whole matrix."""
+    M, K, N = 4096, 3072, 12288
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g)
+    qa, sa = o.fp8_quantize(a.numpy())
+    qw, sw = o.fp8_quantize(w.numpy())
+    tA, tW = torch.from_numpy(qa).to(DEV), torch.from_numpy(qw).to(DEV)
+    rc, C = mm_capi(tA, tW, torch.from_numpy(sa), torch.from_numpy(sw), out_dtype=torch.bfloat16, algo=ALGO_TCGEN05)
+    assert rc == 0
+    rc, C32 = mm_capi(tA, tW, torch.from_numpy(sa), torch.from_numpy(sw), out_dtype=None, algo=ALGO_TCGEN05)
+    assert rc == 0
+    rc, S32 = mm_capi(tA, tW, torch.from_numpy(sa), torch.from_numpy(sw), out_dtype=None, algo=ALGO_SIMT)
+    assert rc == 0
+    e_simt = o.rel_rmse(to_np(C32), to_np(S32))
+    assert e_simt < 1e-4, e_simt
+    ref = o.scaled_mm(qa[:512], qw, sa, sw, out_dtype="bf16", accum="f32")
+    _check(C[:512], ref, torch.bfloat16, what="flux slab")
+    ref64 = o.scaled_mm(qa[-128:], qw[-256:], sa, sw)
+    _check(C32[-128:, -256:], ref64, None, tol=1e-4, what="flux corner fp64")
+    # the reference's own gate: within 15 % of the un-quantised product (test_fp8_metal.py:122)
+    full = (a[:256] @ w.T).numpy()
+    assert o.rel_rmse(to_np(C[:256]), full) < 0.15
+
+
+# ------------------------------------------------------------------ through the reference-shaped API
+
+def test_native_api_shapes_and_asserts():
+    import fp8_mps_native
+    M, K, N = 64, 256, 128                                    # test_fp8_metal.py:128-164
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = (A @ B.T).numpy()
+    qa, sa = fp8_mps_native.fp8_quantize(A)
+    qb, sb = fp8_mps_native.fp8_quantize(B)
+    for fn in (fp8_mps_native.fp8_scaled_mm, fp8_mps_native.fp8_scaled_mm_auto, fp8_mps_native.fp8_scaled_mm_fast):
+        r = fn(qa, qb, sa, sb)
+        assert r.dtype == torch.float32 and r.shape == (M, N) and r.device.type == "cuda"
+        assert o.rel_rmse(to_np(r), ref) < 0.15
+        assert o.rel_rmse(to_np(r), o.scaled_mm(qa.cpu().numpy(), qb.cpu().numpy(), sa.cpu().numpy(), sb.cpu().numpy())) < 1e-4
+    r = fp8_mps_native.fp8_scaled_mm(qa.cpu(), qb.cpu(), sa.cpu(), sb.cpu())      # CPU inputs are moved (native.py:63-70)
+    assert r.device.type == "cuda"
+    with pytest.raises(AssertionError):
+        fp8_mps_native.fp8_scaled_mm(qa.float(), qb, sa, sb)                     # dtype assert (native.py:55)
+    with pytest.raises(AssertionError):
+        fp8_mps_native.fp8_scaled_mm(qa, qb[:, :100].contiguous(), sa, sb)       # K mismatch (native.py:60)
+    with pytest.raises(AssertionError):
+        fp8_mps_native.fp8_scaled_mm(qa.t(), qb, sa, sb)                         # contiguity (native.py:56)
+    lib = fp8_mps_native._get_lib()                                              # bridge ops (fp8_bridge.cpp:361-371)
+    with pytest.raises(RuntimeError):
+        lib.fp8_scaled_mm(qa, qb[:, :100].contiguous(), sa, sb)
+    q2, inv2 = lib.fp8_quantize(A.to(DEV))
+    assert torch.equal(q2, qa) and torch.equal(inv2, sa)
+    # vecmat (test_fp8_metal.py:191-218)
+    x = torch.randn(1, 512, generator=g)
+    W = torch.randn(256, 512, generator=g)
+    xq, xs = fp8_mps_native.fp8_quantize(x)
+    Wq, Ws = fp8_mps_native.fp8_quantize(W)
+    r = fp8_mps_native.fp8_scaled_mm(xq, Wq, xs, Ws)
+    assert r.shape == (1, 256) and o.rel_rmse(to_np(r), (x @ W.T).numpy()) < 0.15
