@@ -257,14 +257,14 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
-        const float sr = e.sr ? __ldg(e.sr) : 1.0f;
+        const float sr = e.sr ? *e.sr : 1.0f;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_idx = (tile % p.num_m_blocks) * kBM;
             const int n_idx = (tile / p.num_m_blocks) * BN;
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
-            const float sa = __ldg(e.sa + (size_t)(m_ok ? m : 0) * e.sa_stride);
+            const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -289,7 +289,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     if (a != a && n < p.N) a = slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)n * p.K, p.K);
                     const int nn = n < p.N ? n : p.N - 1;
                     float x = __fmul_rn(a, sa);
-                    x = __fmul_rn(x, __ldg(e.sb + (size_t)nn * e.sb_stride));
+                    x = __fmul_rn(x, e.sb[(size_t)nn * e.sb_stride]);
                     if (e.bias) x = __fadd_rn(x, epi_bias(e, nn));
                     if (e.sr) x = __fmul_rn(x, sr);
                     v[j] = x;

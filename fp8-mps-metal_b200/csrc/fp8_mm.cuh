@@ -49,17 +49,19 @@ inline Epi make_epi(const MMArgs& a) {
     return e;
 }
 
+// NOTE: plain loads, not __ldg(): nvcc treats ld.global.nc as speculatable and hoisted a guarded
+// `__ldg(bias + n)` above its `if (bias)` check (observed in SASS; a null bias then faults).
 __device__ __forceinline__ float epi_bias(const Epi& e, int n) {
-    if (e.bias_dtype == FP8B_F32) return __ldg(reinterpret_cast<const float*>(e.bias) + n);
-    if (e.bias_dtype == FP8B_F16) return __half2float(__ldg(reinterpret_cast<const __half*>(e.bias) + n));
-    return __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(e.bias) + n));
+    if (e.bias_dtype == FP8B_F32) return reinterpret_cast<const float*>(e.bias)[n];
+    if (e.bias_dtype == FP8B_F16) return __half2float(reinterpret_cast<const __half*>(e.bias)[n]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.bias)[n]);
 }
 
 __device__ __forceinline__ float epi_apply(const Epi& e, float acc, int m, int n) {
-    float v = __fmul_rn(acc, __ldg(e.sa + (size_t)m * e.sa_stride));
-    v = __fmul_rn(v, __ldg(e.sb + (size_t)n * e.sb_stride));
+    float v = __fmul_rn(acc, e.sa[(size_t)m * e.sa_stride]);
+    v = __fmul_rn(v, e.sb[(size_t)n * e.sb_stride]);
     if (e.bias) v = __fadd_rn(v, epi_bias(e, n));
-    if (e.sr) v = __fmul_rn(v, __ldg(e.sr));
+    if (e.sr) v = __fmul_rn(v, *e.sr);
     return v;
 }
 

@@ -172,10 +172,11 @@ def test_full_size_properties():
     g = torch.Generator(device=DEV).manual_seed(11)
     w = (torch.randn(n, generator=g, device=DEV) * 0.02).to(torch.bfloat16)
     q = _encode_capi(w)
-    # (1) idempotence: enc(dec(enc(x))) == enc(x)
+    # (1) idempotence: enc(dec(enc(x))) == enc(x), except 0x80 (-0.0) -> 0x00, the reference's own
+    #     round-trip allow-list (test_fp8_correctness.py:118-131)
     d = _dequant_capi(q, torch.bfloat16)
     q2 = _encode_capi(d)
-    assert torch.equal(q, q2)
+    assert torch.equal(torch.where(q == 0x80, torch.zeros_like(q), q), q2)
     # (2) the encoder never emits a NaN code and never emits -0 for an input that is not negative
     assert int(((q & 0x7F) == 0x7F).sum()) == 0
     assert int(((q == 0x80) & (w >= 0)).sum()) == 0
