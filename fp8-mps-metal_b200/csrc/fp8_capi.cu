@@ -1,6 +1,7 @@
 // C-ABI surface of libfp8_b200.so that is not a kernel file's own: library info, device facts, and
 // the scaled-matmul dispatcher (the analogue of the M-based selection in
 // fp8_mps_native.fp8_scaled_mm / fp8_scaled_mm_auto, fp8_mps_native.py:78-93, :193-210).
+#include <cstdlib>
 #include <mutex>
 #include "fp8_mm.cuh"
 
@@ -29,6 +30,12 @@ const DeviceInfo& device_info()
         info[dev] = d;
     });
     return info[dev];
+}
+
+int tune_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
 }
 
 static int validate(const MMArgs& a)

@@ -24,6 +24,10 @@ inline int after_launch() {
 struct DeviceInfo { int sm_count; int cc_major; int cc_minor; int ok; };
 const DeviceInfo& device_info();
 
+// Developer tuning knob: integer from the environment (read on every call; used by the
+// profiling scripts to A/B kernel variants without rebuilding).  Never changes results.
+int tune_int(const char* name, int dflt);
+
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline size_t dtype_size(int dt) { return dt == FP8B_F32 ? 4 : 2; }
 inline bool valid_dtype(int dt) { return dt == FP8B_F32 || dt == FP8B_F16 || dt == FP8B_BF16; }

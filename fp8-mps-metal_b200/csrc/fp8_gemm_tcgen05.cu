@@ -50,6 +50,7 @@ struct GemmParams {
     int num_m_blocks, num_n_blocks, num_k_blocks;
     Epi epi;
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
+    int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -258,6 +259,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
         const float sr = e.sr ? *e.sr : 1.0f;
+        const float sb0 = e.sb[0];
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_idx = (tile % p.num_m_blocks) * kBM;
@@ -273,28 +275,81 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 uint32_t r[32];
                 __syncwarp();                         // lanes may have diverged on the row/column masks below
                 tmem_ld_x32(t_row + c0, r);
+                const int n0 = n_idx + c0;
+                const bool full_chunk = (n0 + 32 <= p.N) && p.col_vec_ok;      // warp-uniform
+                // per-column parameters of this chunk: one broadcast 16-byte load per 4 columns, issued
+                // while the TMEM load is in flight
+                float sbv[32];
+                float bv[32];
+                if (full_chunk) {
+                    if (e.sb_stride) {
+                        const float4* s4 = reinterpret_cast<const float4*>(e.sb + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 t = s4[j];
+                            sbv[4 * j] = t.x; sbv[4 * j + 1] = t.y; sbv[4 * j + 2] = t.z; sbv[4 * j + 3] = t.w;
+                        }
+                    }
+                    if (e.bias) {
+                        if (e.bias_dtype == FP8B_F32) {
+                            const float4* b4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.bias) + n0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = b4[j];
+                                bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+                            }
+                        } else {
+                            const uint4* b4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.bias) + n0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint4 t = b4[j];
+                                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (e.bias_dtype == FP8B_BF16) {
+                                        bv[8 * j + 2 * i] = __uint_as_float(w[i] << 16);
+                                        bv[8 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+                                    } else {
+                                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                                        bv[8 * j + 2 * i] = f.x; bv[8 * j + 2 * i + 1] = f.y;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
                 tmem_ld_wait();
                 if (c0 + 32 == BN) {                  // last read of this accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(acc));
                 }
-                const int n0 = n_idx + c0;
-                if (!m_ok || n0 >= p.N) continue;
-                float v[32];
+                if (n0 >= p.N) continue;              // warp-uniform
+
+                // NaN-byte fix-up (cold): a NaN accumulator can only come from a 0x7F/0xFF operand byte
+                float nan_probe = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + j;
-                    float a = __uint_as_float(r[j]);
-                    if (a != a && n < p.N) a = slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)n * p.K, p.K);
-                    const int nn = n < p.N ? n : p.N - 1;
-                    float x = __fmul_rn(a, sa);
-                    x = __fmul_rn(x, e.sb[(size_t)nn * e.sb_stride]);
-                    if (e.bias) x = __fadd_rn(x, epi_bias(e, nn));
-                    if (e.sr) x = __fmul_rn(x, sr);
-                    v[j] = x;
+                for (int j = 0; j < 32; ++j) nan_probe += __uint_as_float(r[j]);
+                if (__any_sync(0xFFFFFFFFu, nan_probe != nan_probe)) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = __uint_as_float(r[j]);
+                        if (a != a && m_ok && n0 + j < p.N)
+                            r[j] = __float_as_uint(slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)(n0 + j) * p.K, p.K));
+                    }
                 }
-                if (p.vec_store_ok && n0 + 32 <= p.N) {
+                if (!m_ok) continue;
+
+                if (full_chunk && p.vec_store_ok) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __fmul_rn(__uint_as_float(r[j]), sa);
+                        x = __fmul_rn(x, e.sb_stride ? sbv[j] : sb0);
+                        if (e.bias) x = __fadd_rn(x, bv[j]);
+                        if (e.sr) x = __fmul_rn(x, sr);
+                        v[j] = x;
+                    }
                     if (e.out_dtype == FP8B_F32) {
                         float* dst = reinterpret_cast<float*>(e.C) + (size_t)m * e.ldc + n0;
 #pragma unroll
@@ -318,9 +373,12 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         for (int j = 0; j < 16; j += 4) stg_v4(dst + 2 * j, pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
                     }
                 } else {
+                    // edge chunk / unaligned output: scalar, bounds-checked
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + j < p.N) epi_store(e, m, n0 + j, v[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + j;
+                        if (n < p.N) epi_store(e, m, n, epi_apply(e, __uint_as_float(r[j]), m, n));
+                    }
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -400,6 +458,7 @@ static int launch_tcgen05_bn(const MMArgs& a)
     p.epi = make_epi(a);
     const size_t esz = dtype_size(a.out_dtype);
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
+    p.col_vec_ok = aligned(a.sb, 16) && (!a.bias || aligned(a.bias, 16));
 
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int sms = device_info().sm_count;

@@ -31,7 +31,6 @@ namespace fp8b {
 
 constexpr int kGemvThreads = 256;
 constexpr int kGemvWarps = kGemvThreads / 32;
-constexpr int kGemvUnroll = 4;
 constexpr int kGemvMaxMT = 4;
 constexpr int kGemvMaxSplit = 8;
 constexpr int kGemvMaxSmem = 96 * 1024;
@@ -81,7 +80,7 @@ __device__ __forceinline__ void gemv_consume(const uint4& w, const uint4* __rest
     }
 }
 
-template <int MT>
+template <int MT, int U>
 __global__ void __launch_bounds__(kGemvThreads)
 fp8_gemv_kernel(const GemvParams p)
 {
@@ -105,6 +104,15 @@ fp8_gemv_kernel(const GemvParams p)
         const int len = min(k_end - kp, p.k_panel);
         const int nvec = len >> 4;
         const int nvec_panel = p.k_panel >> 4;
+        const uint8_t* wp = wrow + kp;
+        // first batch of weight vectors goes in flight BEFORE x is staged, so the prologue
+        // (x load + decode + barrier) overlaps the first HBM round trip
+        uint4 cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int vv = lane + 32 * u;
+            cur[u] = (row_ok && vv < nvec) ? ldg_w_v4(wp + (size_t)vv * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
         if (kp != k_begin) __syncthreads();
         // stage x[:, kp : kp+len] as fp16 (raw hardware decode; NaN bytes stay NaN on purpose)
         for (int i = threadIdx.x; i < MT * nvec; i += kGemvThreads) {
@@ -120,18 +128,20 @@ fp8_gemv_kernel(const GemvParams p)
         }
         __syncthreads();
         if (row_ok) {
-            const uint8_t* wp = wrow + kp;
-            int v = lane;
-            for (; v + 32 * (kGemvUnroll - 1) < nvec; v += 32 * kGemvUnroll) {
-                uint4 w[kGemvUnroll];
+            for (int v = lane; v < nvec; v += 32 * U) {
+                uint4 nxt[U];
 #pragma unroll
-                for (int u = 0; u < kGemvUnroll; ++u) w[u] = ldg_w_v4(wp + (size_t)(v + 32 * u) * 16);
+                for (int u = 0; u < U; ++u) {                       // next batch in flight while this one is consumed
+                    const int vv = v + 32 * (U + u);
+                    nxt[u] = vv < nvec ? ldg_w_v4(wp + (size_t)vv * 16) : make_uint4(0u, 0u, 0u, 0u);
+                }
 #pragma unroll
-                for (int u = 0; u < kGemvUnroll; ++u) gemv_consume<MT>(w[u], xs, nvec_panel, v + 32 * u, acc0, acc1);
-            }
-            for (; v < nvec; v += 32) {
-                const uint4 w = ldg_w_v4(wp + (size_t)v * 16);
-                gemv_consume<MT>(w, xs, nvec_panel, v, acc0, acc1);
+                for (int u = 0; u < U; ++u) {
+                    const int vv = v + 32 * u;
+                    if (vv < nvec) gemv_consume<MT>(cur[u], xs, nvec_panel, vv, acc0, acc1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
             }
         }
     }
@@ -198,12 +208,12 @@ fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict
 
 bool gemv_supported(const MMArgs& a) { return a.M >= 1 && a.M <= 16; }
 
-template <int MT>
+template <int MT, int U>
 static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t st)
 {
     static bool attr_set = false;                  // benign race: idempotent attribute write
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fp8_gemv_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem);
+        cudaError_t e = cudaFuncSetAttribute(fp8_gemv_kernel<MT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem);
         if (e != cudaSuccess) return cuda_fail(e);
         attr_set = true;
     }
@@ -217,7 +227,7 @@ static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t 
     attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = S > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemv_kernel<MT>, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemv_kernel<MT, U>, p);
     if (e != cudaSuccess) return cuda_fail(e);
     return after_launch();
 }
@@ -225,6 +235,11 @@ static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t 
 int launch_gemv(const MMArgs& a)
 {
     if (!gemv_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    // kernel choice: M == 1 -> CUDA-core FHFMA kernel (exact fp32 accumulation order per lane);
+    // M >= 2 -> warp-level tensor-core kernel (weights streamed once for all M rows).
+    // FP8B_GEMV_IMPL=1 / 2 forces the first / second (profiling knob).
+    const int impl = tune_int("FP8B_GEMV_IMPL", 0);
+    if (gemv_mma_supported(a) && (impl == 2 || (impl == 0 && a.M >= 2))) return launch_gemv_mma(a);
     const Epi epi = make_epi(a);
     const bool fast = (a.K % 16 == 0) && a.K >= 16 && aligned(a.A, 16) && aligned(a.B, 16);
     if (!fast) {
@@ -249,11 +264,13 @@ int launch_gemv(const MMArgs& a)
         p.k_per_split = kps; p.k_panel = panel; p.epi = epi;
         const size_t smem = (size_t)mt * panel * 2;
         int rc;
+        const int unroll = tune_int("FP8B_GEMV_UNROLL", 4);
         switch (mt) {
-            case 1: rc = launch_gemv_mt<1>(p, S, smem, a.st); break;
-            case 2: rc = launch_gemv_mt<2>(p, S, smem, a.st); break;
-            case 3: rc = launch_gemv_mt<3>(p, S, smem, a.st); break;
-            default: rc = launch_gemv_mt<4>(p, S, smem, a.st); break;
+            case 1: rc = unroll == 2 ? launch_gemv_mt<1, 2>(p, S, smem, a.st)
+                       : unroll == 8 ? launch_gemv_mt<1, 8>(p, S, smem, a.st) : launch_gemv_mt<1, 4>(p, S, smem, a.st); break;
+            case 2: rc = launch_gemv_mt<2, 4>(p, S, smem, a.st); break;
+            case 3: rc = launch_gemv_mt<3, 4>(p, S, smem, a.st); break;
+            default: rc = launch_gemv_mt<4, 4>(p, S, smem, a.st); break;
         }
         if (rc != FP8B_OK) return rc;
     }

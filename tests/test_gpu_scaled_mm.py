@@ -99,6 +99,35 @@ def test_gemv(M, K, N, odt, kw):
         _run_case(M, K, N, odt, ALGO_GEMV, seed=K, kind="bytes", **kw)
 
 
+@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("M,K,N,odt,kw", [
+    (1, 14336, 4096, torch.bfloat16, {}),
+    (1, 4096, 4096, None, {}),
+    (4, 4096, 4096, torch.bfloat16, {"bias_dtype": torch.bfloat16}),
+    (8, 2048, 100, None, {"per_row_a": True, "per_row_b": True}),
+    (9, 1040, 50, torch.float16, {"scale_result": True}),
+    (16, 4096, 24, None, {"per_row_a": True}),
+    (3, 80, 17, None, {}),
+])
+def test_gemv_both_kernels(monkeypatch, impl, M, K, N, odt, kw):
+    """FP8B_GEMV_IMPL=1: CUDA-core FHFMA kernel; =2: warp-level tensor-core kernel.  Both must meet
+    the same tolerance on every M in 1..16."""
+    monkeypatch.setenv("FP8B_GEMV_IMPL", str(impl))
+    _run_case(M, K, N, odt, ALGO_GEMV, seed=impl + M + K + N, **kw)
+
+
+def test_gemv_mma_nan_bytes(monkeypatch):
+    monkeypatch.setenv("FP8B_GEMV_IMPL", "2")
+    rng = np.random.default_rng(1)
+    A = rng.integers(0, 256, (5, 1024), dtype=np.uint8)
+    B = rng.integers(0, 256, (70, 1024), dtype=np.uint8)
+    sa = np.array([0.5], np.float32)
+    sb = np.array([0.25], np.float32)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa), torch.from_numpy(sb))
+    assert rc == 0
+    _check(C, o.scaled_mm(A, B, sa, sb), None, what="mma nan bytes")
+
+
 def test_gemv_matches_reference_summation_to_fp32_noise():
     """Against the plain-C restatement of the shader's own loop order (oracle/fp8_oracle.c):
     same fp32 products, different summation order only."""
