@@ -34,11 +34,15 @@ constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
 constexpr int kGemmThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int kNumEpiWarps = 4;
 
-template <int BN> struct GemmCfg {
+// CG = CTA-group size.  CG == 2: two CTAs of a cluster (an SM pair) compute one 256 x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, so the
+// shared-memory traffic per MMA (operand reads + TMA writes) drops from 24 KB to 16 KB per 128 cycles.
+template <int BN, int CG> struct GemmCfg {
     static constexpr int kABytes = kBM * kBK;
-    static constexpr int kBBytes = BN * kBK;
+    static constexpr int kBRows = BN / CG;                         // B rows staged by one CTA
+    static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
+    static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BN;                       // 512 or 256: a power of two >= 32
     static constexpr int kBarBytes = 256;
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment
@@ -51,6 +55,7 @@ struct GemmParams {
     Epi epi;
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
+    int debug;                               // FP8B_GEMM_DEBUG profiling knob: 1 = no stores, 2 = drain TMEM only
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -139,6 +144,46 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cta_group::2 flavours (a CTA pair; rank 0 of the cluster is the leader) -------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair; the bytes are accounted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // K-major, 128B-swizzled shared-memory operand descriptor (PTX "matrix descriptor", sm_100 version 1):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups      [46,48) version = 1
@@ -165,13 +210,18 @@ __device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t
 
 // ------------------------------------------------------------------------------ kernel
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
                         const GemmParams p)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
+    constexpr int kTileM = kBM * CG;                 // rows of C per tile (per CTA pair when CG == 2)
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    const int worker = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-loop index
+    const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* bar_mem = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -193,16 +243,17 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps * CG); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols);
-        tmem_relinquish();
+        if (CG == 2) { tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols); tmem_relinquish_2sm(); }
+        else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -212,26 +263,33 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m_idx = (tile % p.num_m_blocks) * kBM;
-                const int n_idx = (tile / p.num_m_blocks) * BN;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const int m_idx = (tile % p.num_m_blocks) * kTileM + (int)cta_rank * kBM;
+                const int n_idx = (tile / p.num_m_blocks) * BN + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-                    tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
-                    tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                    if (CG == 2) {
+                        // both CTAs load their halves; all bytes are accounted on the leader's barrier
+                        if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
+                        tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                        tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                    } else {
+                        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                        tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                        tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kBM, BN);
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = make_idesc(kTileM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);           // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -244,12 +302,14 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK);
                         const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK);
-                        umma_f8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+                        if (CG == 2) umma_f8_2sm(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+                        else umma_f8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(empty_bar(stage));                   // smem slot free once these MMAs retire
+                    // smem slot free (in both CTAs of a pair) once these MMAs retire
+                    if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(acc));                         // accumulator complete
+                if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -261,8 +321,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const float sr = e.sr ? *e.sr : 1.0f;
         const float sb0 = e.sb[0];
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_idx = (tile % p.num_m_blocks) * kBM;
+        for (int tile = worker; tile < num_tiles; tile += num_workers) {
+            const int m_idx = (tile % p.num_m_blocks) * kTileM + (int)cta_rank * kBM;
             const int n_idx = (tile / p.num_m_blocks) * BN;
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
@@ -322,9 +382,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (c0 + 32 == BN) {                  // last read of this accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                 }
                 if (n0 >= p.N) continue;              // warp-uniform
+                if (p.debug & 2) continue;
 
                 // NaN-byte fix-up (cold): a NaN accumulator can only come from a 0x7F/0xFF operand byte
                 float nan_probe = 0.0f;
@@ -350,7 +411,12 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         if (e.sr) x = __fmul_rn(x, sr);
                         v[j] = x;
                     }
-                    if (e.out_dtype == FP8B_F32) {
+                    if (p.debug & 1) {
+                        float acc_dbg = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc_dbg += v[j];
+                        if (acc_dbg == 123.456f) reinterpret_cast<float*>(e.C)[0] = acc_dbg;
+                    } else if (e.out_dtype == FP8B_F32) {
                         float* dst = reinterpret_cast<float*>(e.C) + (size_t)m * e.ldc + n0;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
@@ -386,10 +452,11 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while its peer still signals it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -434,47 +501,75 @@ bool tcgen05_supported(const MMArgs& a)
     return a.M >= 1 && a.N >= 1 && a.K >= 16 && (a.K % 16 == 0) && aligned(a.A, 16) && aligned(a.B, 16);
 }
 
-template <int BN>
-static int launch_tcgen05_bn(const MMArgs& a)
+template <int BN, int CG>
+static int launch_tcgen05_cfg(const MMArgs& a)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(fp8_gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        attr_err = cudaFuncSetAttribute(fp8_gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes);
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err);
 
     CUtensorMap tmap_a, tmap_b;
     if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;
-    if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, BN)) return FP8B_ERR_CUDA;
+    if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, Cfg::kBRows)) return FP8B_ERR_CUDA;
 
     GemmParams p;
     p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
-    p.num_m_blocks = (a.M + kBM - 1) / kBM;
+    p.num_m_blocks = (a.M + kBM * CG - 1) / (kBM * CG);
     p.num_n_blocks = (a.N + BN - 1) / BN;
     p.num_k_blocks = (a.K + kBK - 1) / kBK;
     p.epi = make_epi(a);
     const size_t esz = dtype_size(a.out_dtype);
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
-    p.col_vec_ok = aligned(a.sb, 16) && (!a.bias || aligned(a.bias, 16));
+    p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
+    p.debug = tune_int("FP8B_GEMM_DEBUG", 0);
 
     const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const int sms = device_info().sm_count;
-    const int grid = tiles < sms ? tiles : sms;
-    fp8_gemm_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, a.st>>>(tmap_a, tmap_b, p);
+    const int workers_max = device_info().sm_count / CG;            // one CTA (or CTA pair) per SM (pair)
+    const int workers = tiles < workers_max ? tiles : workers_max;
+
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(workers * CG, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = a.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = CG > 1 ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG>, tmap_a, tmap_b, p);
+    if (e != cudaSuccess) return cuda_fail(e);
     return after_launch();
 }
 
 int launch_gemm_tcgen05(const MMArgs& a)
 {
     if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
-    // 128x256 tiles when they fill the machine for at least ~2 waves, else 128x128 (finer tail).
+    // Tile choice.  Prefer CTA pairs (256-row tiles) whenever M and N are large enough for them,
+    // 256-wide when that still leaves >= ~2 waves of tiles, else 128-wide (finer tail).
+    // FP8B_GEMM_CFG forces one: 1 = 128x256 1-CTA, 2 = 128x128 1-CTA, 3 = 256x256 pair, 4 = 256x128 pair.
     const int sms = device_info().sm_count;
-    const long tiles256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
-    if (a.N > 128 && tiles256 >= 2L * sms) return launch_tcgen05_bn<256>(a);
-    return launch_tcgen05_bn<128>(a);
+    int cfg = tune_int("FP8B_GEMM_CFG", 0);
+    if (cfg == 0) {
+        const long t_pair256 = (long)((a.M + 255) / 256) * ((a.N + 255) / 256);
+        const long t_pair128 = (long)((a.M + 255) / 256) * ((a.N + 127) / 128);
+        const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
+        if (a.M > 128 && a.N > 128 && t_pair256 >= 2L * (sms / 2)) cfg = 3;
+        else if (a.M > 128 && a.N >= 128 && t_pair128 >= (sms / 2)) cfg = 4;
+        else if (a.N > 128 && t_256 >= 2L * sms) cfg = 1;
+        else cfg = 2;
+    }
+    switch (cfg) {
+        case 1: return launch_tcgen05_cfg<256, 1>(a);
+        case 3: return launch_tcgen05_cfg<256, 2>(a);
+        case 4: return launch_tcgen05_cfg<128, 2>(a);
+        default: return launch_tcgen05_cfg<128, 1>(a);
+    }
 }
 
 }  // namespace fp8b
