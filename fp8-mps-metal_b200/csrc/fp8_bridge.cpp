@@ -180,6 +180,41 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_quantize(torch::Tensor input)
     return std::make_tuple(out, scales.slice(0, 1, 2));
 }
 
+// Fused compute + exchange for the N-sharded linear: this rank's (M, N_local) block is stored through
+// the NVSwitch multicast address `mc_ptr` (element (0,0) of the full row-major (M, full_N) matrix) at
+// column offset n0, so it lands in every rank's copy.
+void fp8_scaled_mm_multicast(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
+                             c10::optional<torch::Tensor> bias, at::ScalarType out_dtype,
+                             int64_t mc_ptr, int64_t full_N, int64_t n0)
+{
+    TORCH_CHECK(A.dtype() == torch::kUInt8 && B.dtype() == torch::kUInt8, "A and B must be uint8 (FP8 encoded)");
+    TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous CUDA tensors");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "K dimension mismatch between A and B");
+    const int64_t M = A.size(0), K = A.size(1), N = B.size(0);
+    TORCH_CHECK(n0 >= 0 && n0 + N <= full_N, "column block outside the full matrix");
+    c10::cuda::CUDAGuard guard(A.device());
+    torch::Tensor sa = as_device_f32(scale_a, A.device());
+    torch::Tensor sb = as_device_f32(scale_b, A.device());
+    torch::Tensor bias_t;
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = bias->to(A.device()).contiguous().reshape({-1});
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    const int odt = to_fp8b_dtype(out_dtype);
+    const int64_t esz = odt == FP8B_F32 ? 4 : 2;
+    void* c_mc = reinterpret_cast<void*>(static_cast<uintptr_t>(mc_ptr) + static_cast<uintptr_t>(n0 * esz));
+    int rc = fp8b_scaled_mm_multicast(u8_ptr(A), u8_ptr(B), c_mc, odt, (int)M, (int)N, (int)K, full_N,
+                                      sa.data_ptr<float>(), (int)sa.numel(), sb.data_ptr<float>(), (int)sb.numel(),
+                                      bias_ptr, bias_dt, nullptr, current_stream());
+    check_status(rc, "fp8b_scaled_mm_multicast");
+}
+
 int64_t select_algo(torch::Tensor A, torch::Tensor B, at::ScalarType out_dtype)
 {
     return fp8b_scaled_mm_select(u8_ptr(A), u8_ptr(B), nullptr, to_fp8b_dtype(out_dtype), (int)A.size(0), (int)B.size(0),
@@ -204,6 +239,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias") = py::none(),
           py::arg("scale_result") = py::none(), py::arg("out_dtype") = py::none(), py::arg("algo") = 0,
           py::arg("out") = py::none());
+    m.def("fp8_scaled_mm_multicast", &fp8_scaled_mm_multicast,
+          "FP8 scaled matmul storing through an NVSwitch multicast address (N-sharded linear)",
+          py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out_dtype"),
+          py::arg("mc_ptr"), py::arg("full_N"), py::arg("n0"));
     m.def("select_algo", &select_algo, py::arg("A"), py::arg("B"), py::arg("out_dtype"));
     m.def("launch_count", []() { return (uint64_t)fp8b_launch_count(); });
     m.def("version", []() { return fp8b_version(); });

@@ -104,6 +104,7 @@ extern "C" int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int o
     a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
     a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
     a.ws = workspace; a.ws_bytes = workspace_bytes; a.st = (cudaStream_t)stream;
+    a.store_mc = 0;
     int rc = validate(a);
     if (rc != FP8B_OK) return rc;
     if (M == 0 || N == 0) return FP8B_OK;
@@ -115,4 +116,24 @@ extern "C" int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int o
         case FP8B_MM_SIMT: return launch_gemm_simt(a);
         default: return FP8B_ERR_INVALID;
     }
+}
+
+extern "C" int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void* C_multicast, int out_dtype,
+                                        int M, int N, int K, int64_t ldc,
+                                        const float* scale_a, int scale_a_len,
+                                        const float* scale_b, int scale_b_len,
+                                        const void* bias, int bias_dtype,
+                                        const float* scale_result, void* stream)
+{
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C_multicast; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = nullptr; a.ws_bytes = 0; a.st = (cudaStream_t)stream;
+    a.store_mc = 1;
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (M == 0 || N == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    return launch_gemm_tcgen05(a);
 }

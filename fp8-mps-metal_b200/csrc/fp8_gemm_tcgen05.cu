@@ -16,7 +16,7 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f8f6f4 (M=128, N=BN, K=32),
 //               four per k-block; tcgen05.commit releases each smem slot and finally publishes the
 //               accumulator.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
+//   warps 2-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
 //               *scale_result -> out dtype -> 16-byte global stores.  Two accumulators of BN columns
 //               live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the main loop
 //               of tile i+1.
@@ -31,8 +31,8 @@ namespace fp8b {
 constexpr int kBM = 128;          // rows of A per tile = UMMA M
 constexpr int kBK = 128;          // bytes of K per stage = one 128B swizzle span
 constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
-constexpr int kGemmThreads = 192; // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 8;   // two warps per TMEM lane quarter, each taking half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 // CG = CTA-group size.  CG == 2: two CTAs of a cluster (an SM pair) compute one 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, so the
@@ -55,6 +55,7 @@ struct GemmParams {
     Epi epi;
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
+    int store_mc;                            // C is an NVSwitch multicast address: store with multimem.st
     int debug;                               // FP8B_GEMM_DEBUG profiling knob: 1 = no stores, 2 = drain TMEM only
 };
 
@@ -204,8 +205,16 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// mc == 0: ordinary 16-byte global store.  mc != 0: `p` is an NVSwitch MULTICAST address and the store
+// is replicated by the switch into the same offset of every GPU bound to the multicast object
+// (multimem.st) -- the output tile reaches all ranks of an N-sharded linear in one instruction.
+__device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, int mc) {
+    if (mc)
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                     :: "l"(p), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)),
+                        "f"(__uint_as_float(d)) : "memory");
+    else
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // ------------------------------------------------------------------------------ kernel
@@ -315,7 +324,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
+        const int col_half = (warp - 2) >> 2;         // warps 2..5 -> columns [0, BN/2), warps 6..9 -> [BN/2, BN)
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
         const float sr = e.sr ? *e.sr : 1.0f;
@@ -331,7 +341,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
                 uint32_t r[32];
                 __syncwarp();                         // lanes may have diverged on the row/column masks below
                 tmem_ld_x32(t_row + c0, r);
@@ -379,7 +389,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
                 tmem_ld_wait();
-                if (c0 + 32 == BN) {                  // last read of this accumulator: hand it back early
+                if (c0 + 32 == (col_half + 1) * (BN / 2)) {   // this warp's last read of the accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
@@ -421,7 +431,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             stg_v4(dst + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]),
-                                   __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+                                   __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]), p.store_mc);
                     } else {
                         uint32_t pk[16];
 #pragma unroll
@@ -436,7 +446,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                         uint16_t* dst = reinterpret_cast<uint16_t*>(e.C) + (size_t)m * e.ldc + n0;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) stg_v4(dst + 2 * j, pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+                        for (int j = 0; j < 16; j += 4) stg_v4(dst + 2 * j, pk[j], pk[j + 1], pk[j + 2], pk[j + 3], p.store_mc);
                     }
                 } else {
                     // edge chunk / unaligned output: scalar, bounds-checked
@@ -527,6 +537,9 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
     p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
     p.debug = tune_int("FP8B_GEMM_DEBUG", 0);
+    p.store_mc = a.store_mc;
+    // multimem.st has no sub-word form: the multicast mode needs every chunk on the 16-byte path
+    if (a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int workers_max = device_info().sm_count / CG;            // one CTA (or CTA pair) per SM (pair)

@@ -20,6 +20,7 @@ struct MMArgs {
     const void* bias; int bias_dtype;
     const float* sr;
     void* ws; size_t ws_bytes;
+    int store_mc;          // tcgen05 kernel only: C is a multicast address (multimem.st)
     cudaStream_t st;
 };
 

@@ -1,0 +1,143 @@
+"""
+N-sharded FP8 linear across the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference is single-device: this module is the build's multi-GPU extension of its
+`_scaled_mm` path for large-N DiT linears.  The weight B (N,K) is split by ROWS of B = COLUMNS of
+the output: rank r owns B[n0_r:n1_r, :] (and the matching slices of a per-row scale_b and of the
+bias), the activations A (M,K) are replicated, every rank runs the same tcgen05 kernel on its
+shard -- no reduction is needed -- and ONE exchange step assembles the (M,N) result:
+
+  mode="allgather"  ncclAllGather of the contiguous local (M, N/w) blocks into a rank-major
+                    [w, M, N/w] buffer, exposed either as is (layout="rank_major", zero extra
+                    passes) or re-laid to the row-major (M,N) tensor stock _scaled_mm returns
+                    (layout="row_major", one extra device pass);
+  mode="multicast"  fused: the GEMM epilogue writes each output tile straight into the row-major
+                    (M,N) result of EVERY rank through an NVSwitch multicast mapping
+                    (multimem.st), so the exchange overlaps the math tile by tile and no gather or
+                    re-layout pass exists.  Needs torch symmetric memory (CUDA, NVLS).
+
+Shards are contiguous, equal-sized (ceil(N/w) rounded up to `align` columns; the tail shard may be
+short or empty) so the gather can use the fixed-size collective.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(N: int, world: int, rank: int, align: int = 16) -> Tuple[int, int, int]:
+    """(n0, n1, width): rank's column range [n0, n1) and the common padded shard width."""
+    width = -(-N // world)
+    width = -(-width // align) * align
+    n0 = min(N, rank * width)
+    n1 = min(N, n0 + width)
+    return n0, n1, width
+
+
+def _default_mm(a, b, sa, sb, bias, out_dtype, out=None):
+    import fp8_mps_native
+    return fp8_mps_native.fp8_scaled_mm_fused(a, b, sa, sb, bias=bias, scale_result=None, out_dtype=out_dtype, out=out)
+
+
+class ShardedScaledMM:
+    """y = _scaled_mm(x, W^T) with W (N,K) row-sharded over the process group."""
+
+    def __init__(self, weight_u8: torch.Tensor, scale_b: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 group=None, mm_fn: Optional[Callable] = None, weight_is_shard: bool = False,
+                 full_N: Optional[int] = None, align: int = 16):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.mm_fn = mm_fn or _default_mm
+        if weight_is_shard:
+            assert full_N is not None
+            self.N = int(full_N)
+        else:
+            self.N = int(weight_u8.shape[0])
+        self.n0, self.n1, self.width = shard_bounds(self.N, self.world, self.rank, align)
+        if weight_is_shard:
+            assert weight_u8.shape[0] == self.n1 - self.n0
+            self.weight = weight_u8.contiguous()
+        else:
+            self.weight = weight_u8[self.n0:self.n1].contiguous()
+        sb = scale_b.reshape(-1)
+        if sb.numel() == 1:
+            self.scale_b = sb
+        elif sb.numel() == self.N:
+            self.scale_b = sb[self.n0:self.n1].contiguous()
+        else:
+            assert sb.numel() == self.n1 - self.n0, "scale_b must have 1, N or shard-width elements"
+            self.scale_b = sb.contiguous()
+        if bias is None:
+            self.bias = None
+        elif bias.numel() == self.N:
+            self.bias = bias.reshape(-1)[self.n0:self.n1].contiguous()
+        else:
+            assert bias.numel() == self.n1 - self.n0
+            self.bias = bias.reshape(-1).contiguous()
+        self._symm = None
+
+    # ------------------------------------------------------------------ local compute
+    def local(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16, out=None) -> torch.Tensor:
+        """This rank's (M, n1-n0) column block."""
+        if self.n1 == self.n0:
+            return torch.empty(x_u8.shape[0], 0, dtype=out_dtype or torch.float32, device=x_u8.device)
+        return self.mm_fn(x_u8, self.weight, scale_a, self.scale_b, self.bias, out_dtype, out)
+
+    # ------------------------------------------------------------------ NCCL all-gather path
+    def __call__(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16,
+                 layout: str = "row_major", mode: str = "allgather") -> torch.Tensor:
+        if mode == "multicast":
+            return self.forward_multicast(x_u8, scale_a, out_dtype)
+        M = x_u8.shape[0]
+        odt = out_dtype or torch.float32
+        if self.world == 1:
+            return self.local(x_u8, scale_a, out_dtype)
+        gathered = torch.empty(self.world, M, self.width, dtype=odt, device=x_u8.device)
+        mine = gathered[self.rank]                              # contiguous (M, width) block
+        if self.n1 - self.n0 == self.width:
+            self.local(x_u8, scale_a, out_dtype, out=mine)      # the kernel writes straight into the gather buffer
+        else:                                                   # short tail shard: pad with zeros
+            mine.zero_()
+            if self.n1 > self.n0:
+                mine[:, : self.n1 - self.n0].copy_(self.local(x_u8, scale_a, out_dtype))
+        inp = mine.reshape(-1)                                  # NCCL gathers in place (input aliases its output slot)
+        if dist.get_backend(self.group) != "nccl":
+            inp = inp.clone()
+        dist.all_gather_into_tensor(gathered.view(-1), inp, group=self.group)
+        if layout == "rank_major":
+            return gathered                                     # [w, M, width]; column n lives at [n // width, :, n % width]
+        return gathered.permute(1, 0, 2).reshape(M, self.world * self.width)[:, : self.N].contiguous()
+
+    # ------------------------------------------------------------------ fused multicast path
+    def _symm_buffer(self, M: int, odt, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (M, odt)
+        if self._symm is None or self._symm[0] != key:
+            buf = symm_mem.empty((M, self.N), dtype=odt, device=device)
+            hdl = symm_mem.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            self._symm = (key, buf, hdl)
+        return self._symm[1], self._symm[2]
+
+    def forward_multicast(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """GEMM whose epilogue stores through the NVSwitch multicast address: after the closing
+        barrier every rank holds the full row-major (M,N) result.  The returned tensor aliases a
+        symmetric buffer that the next call overwrites."""
+        import fp8_mps_native
+        M = x_u8.shape[0]
+        odt = out_dtype or torch.float32
+        if self.world == 1:
+            return self.local(x_u8, scale_a, out_dtype)
+        buf, hdl = self._symm_buffer(M, odt, x_u8.device)
+        mc = getattr(hdl, "multicast_ptr", 0)
+        if not mc:
+            raise RuntimeError("symmetric memory has no multicast mapping on this system (NVLS unavailable)")
+        hdl.barrier(channel=0)                                  # peers are done reading the previous result
+        if self.n1 > self.n0:
+            fp8_mps_native._get_lib().fp8_scaled_mm_multicast(
+                x_u8, self.weight, scale_a, self.scale_b, self.bias, odt, int(mc), int(self.N), int(self.n0))
+        hdl.barrier(channel=1)                                  # every rank's tiles have landed everywhere
+        return buf

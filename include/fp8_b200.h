@@ -144,6 +144,24 @@ FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out
 
 FP8B_API size_t fp8b_scaled_mm_workspace_bytes(int M, int N, int K);
 
+/*
+ * fp8b_scaled_mm (tcgen05 kernel) whose output pointer is an NVSwitch MULTICAST address -- the
+ * fused compute + exchange step of an N-sharded linear (no reference counterpart; the reference is
+ * single-device).  C_multicast addresses element (0,0) of this rank's column block inside a
+ * multicast mapping (cuMulticast* / torch symmetric memory `multicast_ptr`) of a row-major (M, ldc)
+ * matrix that exists on every GPU of the group: the epilogue stores each tile with multimem.st, so
+ * the switch replicates it into every GPU's copy while the next tile is being computed.
+ * The caller orders ranks around the call (a barrier before reuse of the buffer and one after).
+ * Requires N % 32 == 0, 16-byte aligned C_multicast / ldc / scale_b / bias, and the TMA alignment
+ * rules of the tcgen05 kernel; otherwise FP8B_ERR_UNSUPPORTED.
+ */
+FP8B_API int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void* C_multicast, int out_dtype,
+                             int M, int N, int K, int64_t ldc,
+                             const float* scale_a, int scale_a_len,
+                             const float* scale_b, int scale_b_len,
+                             const void* bias, int bias_dtype,
+                             const float* scale_result, void* stream);
+
 /* The algorithm FP8B_MM_AUTO resolves to for this problem (pointers supply the alignment). */
 FP8B_API int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const void* C, int out_dtype,
                           int M, int N, int K, int64_t ldc);

@@ -1,0 +1,86 @@
+"""CPU, world_size 2 over gloo: the host logic of the N-sharded linear (partitioning, padding of a
+short tail shard, all-gather layout, row-major re-layout).  The per-rank matmul is injected -- here the
+oracle stands in for the CUDA kernel, which is exactly what a checker may do in tests/."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle_mm(a, b, sa, sb, bias, out_dtype, out=None):
+    import fp8_oracle as o
+    name = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16", None: "f32"}[out_dtype]
+    r = o.scaled_mm(a.numpy(), b.numpy(), sa.numpy(), sb.numpy(), None if bias is None else bias.float().numpy(),
+                    None, name)
+    t = torch.from_numpy(r).to(out_dtype or torch.float32)
+    if out is not None:
+        out.copy_(t)
+        return out
+    return t
+
+
+def _worker(rank, world, port, N, per_row, with_bias, results):
+    for p in (ROOT, os.path.join(ROOT, "fp8-mps-metal_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fp8_oracle as o
+        from fp8_sharded import ShardedScaledMM, shard_bounds
+        rng = np.random.default_rng(123)
+        M, K = 5, 64
+        A = rng.integers(0, 127, (M, K), dtype=np.uint8)
+        W = rng.integers(0, 127, (N, K), dtype=np.uint8)
+        sa = np.array([0.5], np.float32)
+        sb = (rng.random(N).astype(np.float32) + 0.5) if per_row else np.array([0.25], np.float32)
+        bias = rng.standard_normal(N).astype(np.float32) if with_bias else None
+        lin = ShardedScaledMM(torch.from_numpy(W), torch.from_numpy(sb), None if bias is None else torch.from_numpy(bias),
+                              mm_fn=_oracle_mm)
+        n0, n1, width = shard_bounds(N, world, rank)
+        assert (lin.n0, lin.n1, lin.width) == (n0, n1, width)
+        y = lin(torch.from_numpy(A), torch.from_numpy(sa), out_dtype=torch.float32)
+        ref = o.scaled_mm(A, W, sa, sb, bias)
+        ok_row = bool(y.shape == (M, N) and np.array_equal(y.numpy(), ref) and y.is_contiguous())
+        g = lin(torch.from_numpy(A), torch.from_numpy(sa), out_dtype=torch.float32, layout="rank_major")
+        ok_rank = g.shape == (world, M, width)
+        for n in range(N):
+            ok_rank = ok_rank and np.array_equal(g[n // width, :, n % width].numpy(), ref[:, n])
+        # a rank holding only its shard of the weight builds the same object
+        lin2 = ShardedScaledMM(torch.from_numpy(W[n0:n1].copy()), torch.from_numpy(sb if sb.size == 1 else sb[n0:n1].copy()),
+                               None if bias is None else torch.from_numpy(bias[n0:n1].copy()), mm_fn=_oracle_mm,
+                               weight_is_shard=True, full_N=N)
+        y2 = lin2(torch.from_numpy(A), torch.from_numpy(sa), out_dtype=torch.float32)
+        results[rank] = ok_row and bool(ok_rank) and bool(np.array_equal(y2.numpy(), ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,per_row,with_bias", [(64, False, False), (96, True, True), (40, True, False), (17, False, True)])
+def test_sharded_linear_world2_gloo(N, per_row, with_bias):
+    world = 2
+    port = 29500 + (os.getpid() + N) % 2000
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, port, N, per_row, with_bias, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+def test_shard_bounds_cover_and_align():
+    sys.path.insert(0, os.path.join(ROOT, "fp8-mps-metal_b200"))
+    from fp8_sharded import shard_bounds
+    for N in (12288, 1536, 100, 17, 16, 1):
+        for w in (1, 2, 4, 8):
+            cover = []
+            for r in range(w):
+                n0, n1, width = shard_bounds(N, w, r)
+                assert width % 16 == 0 and 0 <= n0 <= n1 <= N and n1 - n0 <= width
+                cover += list(range(n0, n1))
+            assert cover == list(range(N))
+    assert shard_bounds(12288, 8, 3) == (4608, 6144, 1536)
