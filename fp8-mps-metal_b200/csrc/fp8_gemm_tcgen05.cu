@@ -16,7 +16,7 @@
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f8f6f4 (M=128, N=BN, K=32),
 //               four per k-block; tcgen05.commit releases each smem slot and finally publishes the
 //               accumulator.
-//   warps 2-9   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
+//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
 //               *scale_result -> out dtype -> 16-byte global stores.  Two accumulators of BN columns
 //               live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the main loop
 //               of tile i+1.
@@ -31,8 +31,11 @@ namespace fp8b {
 constexpr int kBM = 128;          // rows of A per tile = UMMA M
 constexpr int kBK = 128;          // bytes of K per stage = one 128B swizzle span
 constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
-constexpr int kNumEpiWarps = 8;   // two warps per TMEM lane quarter, each taking half of the tile's columns
-constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// Epilogue warps: a multiple of 4 (one per TMEM lane quarter); with 8 the two warps of a quarter split the
+// tile's columns.  Measured on C4 (256x256 pair tiles): 4 warps 113.1 us, 8 warps 119.3 us -> 4.
+constexpr int kNumEpiWarps = 4;
+constexpr int kEpiColSplits = kNumEpiWarps / 4;
+constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;   // warp 0 TMA, warp 1 MMA, the rest epilogue
 
 // CG = CTA-group size.  CG == 2: two CTAs of a cluster (an SM pair) compute one 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, so the
@@ -325,7 +328,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
-        const int col_half = (warp - 2) >> 2;         // warps 2..5 -> columns [0, BN/2), warps 6..9 -> [BN/2, BN)
+        const int col_part = (warp - 2) >> 2;         // which slice of the tile's columns this warp drains
+        constexpr int kColsPerWarp = BN / kEpiColSplits;
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
         const float sr = e.sr ? *e.sr : 1.0f;
@@ -341,7 +345,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
+            for (int c0 = col_part * kColsPerWarp; c0 < (col_part + 1) * kColsPerWarp; c0 += 32) {
                 uint32_t r[32];
                 __syncwarp();                         // lanes may have diverged on the row/column masks below
                 tmem_ld_x32(t_row + c0, r);
@@ -389,7 +393,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
                 tmem_ld_wait();
-                if (c0 + 32 == (col_half + 1) * (BN / 2)) {   // this warp's last read of the accumulator: hand it back early
+                if (c0 + 32 == (col_part + 1) * kColsPerWarp) {   // this warp's last read of the accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
