@@ -33,7 +33,7 @@ constexpr int kBK = 128;          // bytes of K per stage = one 128B swizzle spa
 constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
 // Epilogue warps: a multiple of 4 (one per TMEM lane quarter); with 8 the two warps of a quarter split the
 // tile's columns.  Measured on C4 (256x256 pair tiles): 4 warps 113.1 us, 8 warps 119.3 us -> 4.
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 4;   // the staging buffer below is sized for 4
 constexpr int kEpiColSplits = kNumEpiWarps / 4;
 constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;   // warp 0 TMA, warp 1 MMA, the rest epilogue
 
@@ -48,7 +48,8 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BN;                       // 512 or 256: a power of two >= 32
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // +1024: manual alignment
+    static constexpr int kEpiStageBytes = 4 * 8192;                // per epilogue warp: 32 rows x 256 B, XOR-swizzled
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;   // +1024: manual alignment
 };
 
 struct GemmParams {
@@ -220,6 +221,13 @@ __device__ __forceinline__ void stg_v4(void* p, uint32_t a, uint32_t b, uint32_t
         asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
 // ------------------------------------------------------------------------------ kernel
 
 template <int BN, int CG>
@@ -245,6 +253,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_mem + 8 * (2 * Cfg::kStages + 4));
+    const uint32_t stage_base = bar_base + Cfg::kBarBytes;         // epilogue staging tiles (16-byte aligned)
 
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -413,8 +422,6 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             r[j] = __float_as_uint(slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)(n0 + j) * p.K, p.K));
                     }
                 }
-                if (!m_ok) continue;
-
                 if (full_chunk && p.vec_store_ok) {
                     float v[32];
 #pragma unroll
@@ -425,19 +432,13 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         if (e.sr) x = __fmul_rn(x, sr);
                         v[j] = x;
                     }
-                    if (p.debug & 1) {
-                        float acc_dbg = 0.0f;
+                    // pack to the output dtype: 8 (f32) or 4 (f16/bf16) 16-byte pieces per lane
+                    uint32_t pk[32];
+                    const bool is_f32 = e.out_dtype == FP8B_F32;
+                    if (is_f32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc_dbg += v[j];
-                        if (acc_dbg == 123.456f) reinterpret_cast<float*>(e.C)[0] = acc_dbg;
-                    } else if (e.out_dtype == FP8B_F32) {
-                        float* dst = reinterpret_cast<float*>(e.C) + (size_t)m * e.ldc + n0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            stg_v4(dst + j, __float_as_uint(v[j]), __float_as_uint(v[j + 1]),
-                                   __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]), p.store_mc);
+                        for (int j = 0; j < 32; ++j) pk[j] = __float_as_uint(v[j]);
                     } else {
-                        uint32_t pk[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             if (e.out_dtype == FP8B_BF16) {
@@ -448,11 +449,48 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
                             }
                         }
-                        uint16_t* dst = reinterpret_cast<uint16_t*>(e.C) + (size_t)m * e.ldc + n0;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) stg_v4(dst + 2 * j, pk[j], pk[j + 1], pk[j + 2], pk[j + 3], p.store_mc);
                     }
-                } else {
+                    // Row groups of 256 bytes (128 16-bit or 64 fp32 columns) are staged through a per-warp
+                    // XOR-swizzled shared-memory tile and written out with 16 lanes per row, so every
+                    // store instruction covers 2 rows x 256 contiguous bytes (full 128-byte lines) -- for
+                    // local HBM and, in multicast mode, for NVLink, where 16-byte-per-row scatter is fatal.
+                    const int cpg = is_f32 ? 2 : 4;                      // 32-column chunks per row group
+                    const int ppc = is_f32 ? 8 : 4;                      // 16-byte pieces per chunk per row
+                    const int cg = (c0 >> 5) & (cpg - 1);                // chunk index inside its group
+                    const int ng0 = n0 - cg * 32;                        // first column of the group
+                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4);   // warp-uniform
+                    if (staged) {
+                        const uint32_t st_base = stage_base + (uint32_t)(warp - 2) * 8192u + (uint32_t)lane * 256u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < ppc) {
+                                const uint32_t phys = (uint32_t)((cg * ppc + j) ^ (lane & 15));
+                                sts_v4(st_base + phys * 16u, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            }
+                        }
+                        if (cg == cpg - 1) {
+                            __syncwarp();
+                            const int esz = is_f32 ? 4 : 2;
+                            const int piece = lane & 15;
+                            uint8_t* cbase = reinterpret_cast<uint8_t*>(e.C) + (size_t)ng0 * esz + (size_t)piece * 16;
+#pragma unroll 4
+                            for (int i = 0; i < 16; ++i) {
+                                const int rr = 2 * i + (lane >> 4);
+                                const int gm = m_idx + q * 32 + rr;
+                                uint32_t a0, a1, a2, a3;
+                                lds_v4(stage_base + (uint32_t)(warp - 2) * 8192u + (uint32_t)rr * 256u +
+                                       (uint32_t)((piece ^ (rr & 15)) * 16), a0, a1, a2, a3);
+                                if (gm < p.M) stg_v4(cbase + (size_t)gm * e.ldc * esz, a0, a1, a2, a3, p.store_mc);
+                            }
+                            __syncwarp();
+                        }
+                    } else if (m_ok && !(p.debug & 1)) {
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(e.C) + ((size_t)m * e.ldc + n0) * (is_f32 ? 4 : 2);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < ppc) stg_v4(dst + 16 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3], p.store_mc);
+                    }
+                } else if (m_ok) {
                     // edge chunk / unaligned output: scalar, bounds-checked
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
