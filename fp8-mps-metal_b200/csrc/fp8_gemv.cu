@@ -240,6 +240,7 @@ int launch_gemv(const MMArgs& a)
     // FP8B_GEMV_IMPL=1 / 2 forces the first / second (profiling knob).
     const int impl = tune_int("FP8B_GEMV_IMPL", 0);
     if (gemv_mma_supported(a) && (impl == 2 || (impl == 0 && a.M >= 2))) return launch_gemv_mma(a);
+    if (gemv_rows_supported(a) && (impl == 3)) return launch_gemv_rows(a);
     const Epi epi = make_epi(a);
     const bool fast = (a.K % 16 == 0) && a.K >= 16 && aligned(a.A, 16) && aligned(a.B, 16);
     if (!fast) {

@@ -116,6 +116,33 @@ def test_gemv_both_kernels(monkeypatch, impl, M, K, N, odt, kw):
     _run_case(M, K, N, odt, ALGO_GEMV, seed=impl + M + K + N, **kw)
 
 
+@pytest.mark.parametrize("K,N,odt,kw", [
+    (14336, 4096, torch.bfloat16, {}),
+    (4096, 4096, torch.float16, {"per_row_b": True, "bias_dtype": torch.float16}),
+    (512, 300, None, {}),                       # 2 vectors per warp, ragged rows per CTA
+    (30000, 1000, None, {"scale_result": True}),  # K % 512 != 0, 4 vectors per lane
+    (16, 2000, None, {}),
+])
+def test_gemv_rows_kernel(monkeypatch, K, N, odt, kw):
+    """FP8B_GEMV_IMPL=3: the SM-balanced persistent M=1 kernel (falls back to the warp-per-row kernel
+    where it does not apply, e.g. N < 2 x SM count)."""
+    monkeypatch.setenv("FP8B_GEMV_IMPL", "3")
+    _run_case(1, K, N, odt, ALGO_GEMV, seed=K + N, **kw)
+
+
+def test_gemv_rows_nan_bytes(monkeypatch):
+    monkeypatch.setenv("FP8B_GEMV_IMPL", "3")
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 256, (1, 2048), dtype=np.uint8)
+    B = rng.integers(0, 256, (600, 2048), dtype=np.uint8)
+    A[0, 5] = 0x7F
+    sa = np.array([0.5], np.float32)
+    sb = np.array([0.25], np.float32)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa), torch.from_numpy(sb))
+    assert rc == 0
+    _check(C, o.scaled_mm(A, B, sa, sb), None, what="rows nan bytes")
+
+
 def test_gemv_mma_nan_bytes(monkeypatch):
     monkeypatch.setenv("FP8B_GEMV_IMPL", "2")
     rng = np.random.default_rng(1)
