@@ -245,6 +245,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("mc_ptr"), py::arg("full_N"), py::arg("n0"));
     m.def("select_algo", &select_algo, py::arg("A"), py::arg("B"), py::arg("out_dtype"));
     m.def("launch_count", []() { return (uint64_t)fp8b_launch_count(); });
+    m.def("set_option", [](int option, int value) { check_status(fp8b_set_option(option, value), "fp8b_set_option"); });
+    m.def("get_option", [](int option) { return fp8b_get_option(option); });
+    m.attr("OPT_PDL") = (int)FP8B_OPT_PDL;
+    m.attr("OPT_STATIC_WEIGHTS") = (int)FP8B_OPT_STATIC_WEIGHTS;
     m.def("version", []() { return fp8b_version(); });
     m.attr("ALGO_AUTO") = (int)FP8B_MM_AUTO;
     m.attr("ALGO_GEMV") = (int)FP8B_MM_GEMV;

@@ -8,6 +8,8 @@
 namespace fp8b {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_opt_pdl{1};
+std::atomic<int> g_opt_static_weights{0};
 thread_local int t_last_cuda_error = 0;
 
 const DeviceInfo& device_info()
@@ -74,6 +76,24 @@ extern "C" const char* fp8b_status_string(int status)
         case FP8B_ERR_CUDA: return "CUDA call failed (see fp8b_last_cuda_error)";
         case FP8B_ERR_NO_DEVICE: return "current device is not an sm_100 (B200-class) GPU";
         default: return "unknown status";
+    }
+}
+
+extern "C" int fp8b_set_option(int option, int value)
+{
+    switch (option) {
+        case FP8B_OPT_PDL: g_opt_pdl.store(value ? 1 : 0); return FP8B_OK;
+        case FP8B_OPT_STATIC_WEIGHTS: g_opt_static_weights.store(value ? 1 : 0); return FP8B_OK;
+        default: return FP8B_ERR_INVALID;
+    }
+}
+
+extern "C" int fp8b_get_option(int option)
+{
+    switch (option) {
+        case FP8B_OPT_PDL: return g_opt_pdl.load();
+        case FP8B_OPT_STATIC_WEIGHTS: return g_opt_static_weights.load();
+        default: return FP8B_ERR_INVALID;
     }
 }
 

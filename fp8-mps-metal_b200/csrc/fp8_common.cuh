@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
+#include <utility>
 #include "../../include/fp8_b200.h"
 
 namespace fp8b {
@@ -27,6 +28,42 @@ const DeviceInfo& device_info();
 // Developer tuning knob: integer from the environment (read on every call; used by the
 // profiling scripts to A/B kernel variants without rebuilding).  Never changes results.
 int tune_int(const char* name, int dflt);
+
+// Library options (fp8b_set_option)
+extern std::atomic<int> g_opt_pdl;
+extern std::atomic<int> g_opt_static_weights;
+
+// Launch with optional cluster dimensions and programmatic dependent launch.
+template <typename... KArgs, typename... Args>
+inline int launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     int cluster_x, int cluster_y, bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (cluster_x * cluster_y > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = cluster_y; attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = attr; cfg.numAttrs = n;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return after_launch();
+}
+
+#ifdef __CUDACC__
+// Programmatic dependent launch, device side.  Both are no-ops when the kernel was not launched with
+// the PDL attribute (or has no predecessor).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 inline size_t dtype_size(int dt) { return dt == FP8B_F32 ? 4 : 2; }

@@ -42,6 +42,7 @@ struct GemvParams {
     int N, K;
     int k_per_split;       // multiple of 16
     int k_panel;           // multiple of 16; smem holds MT * k_panel fp16
+    int static_b;          // FP8B_OPT_STATIC_WEIGHTS: B may be read before the predecessor kernel completes
     Epi epi;
 };
 
@@ -100,6 +101,13 @@ fp8_gemv_kernel(const GemvParams p)
 #pragma unroll
     for (int m = 0; m < MT; ++m) { acc0[m] = 0.0f; acc1[m] = 0.0f; }
 
+    // Programmatic dependent launch (see fp8_b200.h, FP8B_OPT_STATIC_WEIGHTS): the next kernel may start
+    // scheduling now; we wait for our predecessor before reading anything it may have written -- all
+    // inputs by default, everything except the weights when they are declared static.
+    pdl_launch_dependents();
+    bool need_wait = p.static_b != 0;
+    if (!need_wait) pdl_wait();
+
     for (int kp = k_begin; kp < k_end; kp += p.k_panel) {
         const int len = min(k_end - kp, p.k_panel);
         const int nvec = len >> 4;
@@ -113,6 +121,7 @@ fp8_gemv_kernel(const GemvParams p)
             const int vv = lane + 32 * u;
             cur[u] = (row_ok && vv < nvec) ? ldg_w_v4(wp + (size_t)vv * 16) : make_uint4(0u, 0u, 0u, 0u);
         }
+        if (need_wait) { pdl_wait(); need_wait = false; }
         if (kp != k_begin) __syncthreads();
         // stage x[:, kp : kp+len] as fp16 (raw hardware decode; NaN bytes stay NaN on purpose)
         for (int i = threadIdx.x; i < MT * nvec; i += kGemvThreads) {
@@ -146,6 +155,7 @@ fp8_gemv_kernel(const GemvParams p)
         }
     }
 
+    if (need_wait) pdl_wait();                       // empty K range: still order the stores below
     float s[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
@@ -217,19 +227,9 @@ static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t 
         if (e != cudaSuccess) return cuda_fail(e);
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((p.N + kGemvWarps - 1) / kGemvWarps, S, 1);
-    cfg.blockDim = dim3(kGemvThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = S; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = S > 1 ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemv_kernel<MT, U>, p);
-    if (e != cudaSuccess) return cuda_fail(e);
-    return after_launch();
+    const bool pdl = p.static_b != 0;
+    return launch_ex(fp8_gemv_kernel<MT, U>, dim3((p.N + kGemvWarps - 1) / kGemvWarps, S, 1), dim3(kGemvThreads, 1, 1),
+                     smem, st, 1, S, pdl, p);
 }
 
 int launch_gemv(const MMArgs& a)
@@ -263,6 +263,7 @@ int launch_gemv(const MMArgs& a)
         GemvParams p;
         p.A = a.A + (size_t)m0 * a.K; p.B = a.B; p.m0 = m0; p.N = a.N; p.K = a.K;
         p.k_per_split = kps; p.k_panel = panel; p.epi = epi;
+        p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && g_opt_static_weights.load(std::memory_order_relaxed)) ? 1 : 0;
         const size_t smem = (size_t)mt * panel * 2;
         int rc;
         const int unroll = tune_int("FP8B_GEMV_UNROLL", 4);

@@ -24,13 +24,13 @@ namespace fp8b {
 constexpr int kMmaThreads = 256;
 constexpr int kMmaWarps = kMmaThreads / 32;
 constexpr int kMmaRows = 16;           // weight rows per CTA (the m16 of the MMA)
-constexpr int kMmaBatch = 4;           // 64-byte k-steps whose loads are issued together
 
 struct GemvMmaParams {
     const uint8_t* A;
     const uint8_t* B;
     int M, N, K;
     int k_per_warp;                    // multiple of 64
+    int static_b;                      // FP8B_OPT_STATIC_WEIGHTS: B may be read before the predecessor completes
     Epi epi;
 };
 
@@ -54,7 +54,7 @@ __device__ __forceinline__ void mma_e4m3_m16n8k32(float (&c)[4], uint32_t a0, ui
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NB>                       // NB = 1: M <= 8, NB = 2: M <= 16
+template <int NB, int BATCH>            // NB = 1: M <= 8, NB = 2: M <= 16; BATCH 64-byte k-steps per load group
 __global__ void __launch_bounds__(kMmaThreads)
 fp8_gemv_mma_kernel(const GemvMmaParams p)
 {
@@ -81,25 +81,53 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
     const int k_hi = min(K, k_lo + p.k_per_warp);
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
 
-    for (int kb = k_lo; kb < k_hi; kb += 64 * kMmaBatch) {
-        uint4 wa[kMmaBatch], wb[kMmaBatch], xa[kMmaBatch], xb[kMmaBatch];
+    uint4 wa[BATCH], wb[BATCH], xa[BATCH], xb[BATCH];
+    auto load_w = [&](uint4 (&a)[BATCH], uint4 (&b)[BATCH], int kb) {
 #pragma unroll
-        for (int s = 0; s < kMmaBatch; ++s) {
+        for (int s = 0; s < BATCH; ++s) {
             const int off = kb + 64 * s;
             const bool ok = off + 16 * t < k_hi;                 // k_hi is a multiple of 16
-            wa[s] = ok ? ldg_stream16(w0 + off) : zero4;
-            wb[s] = ok ? ldg_stream16(w1 + off) : zero4;
-            xa[s] = (ok && xa_ok) ? ldg_cached16(x0 + off) : zero4;
-            if (NB == 2) xb[s] = (ok && xb_ok) ? ldg_cached16(x1 + off) : zero4;
+            a[s] = ok ? ldg_stream16(w0 + off) : zero4;
+            b[s] = ok ? ldg_stream16(w1 + off) : zero4;
         }
+    };
+    auto load_x = [&](uint4 (&a)[BATCH], uint4 (&b)[BATCH], int kb) {
 #pragma unroll
-        for (int s = 0; s < kMmaBatch; ++s) {
+        for (int s = 0; s < BATCH; ++s) {
+            const int off = kb + 64 * s;
+            const bool ok = off + 16 * t < k_hi;
+            a[s] = (ok && xa_ok) ? ldg_cached16(x0 + off) : zero4;
+            if (NB == 2) b[s] = (ok && xb_ok) ? ldg_cached16(x1 + off) : zero4;
+        }
+    };
+
+    // Programmatic dependent launch: let the next kernel on the stream start scheduling now.  With
+    // static weights the first group of B goes in flight BEFORE we wait for the predecessor (whose
+    // output is typically our x); everything the predecessor may have written is read after the wait.
+    pdl_launch_dependents();
+    if (!p.static_b) pdl_wait();
+    load_w(wa, wb, k_lo);
+    if (p.static_b) pdl_wait();
+    load_x(xa, xb, k_lo);
+
+    for (int kb = k_lo; kb < k_hi; kb += 64 * BATCH) {
+        // next group in flight while this one is multiplied
+        uint4 nwa[BATCH], nwb[BATCH], nxa[BATCH], nxb[BATCH];
+        load_w(nwa, nwb, kb + 64 * BATCH);
+        load_x(nxa, nxb, kb + 64 * BATCH);
+#pragma unroll
+        for (int s = 0; s < BATCH; ++s) {
             mma_e4m3_m16n8k32(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
             mma_e4m3_m16n8k32(c[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
             if (NB == 2) {
                 mma_e4m3_m16n8k32(c[1], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xb[s].x, xb[s].y);
                 mma_e4m3_m16n8k32(c[1], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xb[s].z, xb[s].w);
             }
+        }
+#pragma unroll
+        for (int s = 0; s < BATCH; ++s) {
+            wa[s] = nwa[s]; wb[s] = nwb[s]; xa[s] = nxa[s];
+            if (NB == 2) xb[s] = nxb[s];
         }
     }
 
@@ -137,10 +165,16 @@ int launch_gemv_mma(const MMArgs& a)
     p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
     p.k_per_warp = (((a.K + kMmaWarps - 1) / kMmaWarps) + 63) & ~63;
     p.epi = make_epi(a);
+    p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && g_opt_static_weights.load(std::memory_order_relaxed)) ? 1 : 0;
+    const bool pdl = p.static_b != 0;      // without static weights PDL only hides launch latency, which graphs already do
     const int grid = (a.N + kMmaRows - 1) / kMmaRows;
-    if (a.M <= 8) fp8_gemv_mma_kernel<1><<<grid, kMmaThreads, 0, a.st>>>(p);
-    else fp8_gemv_mma_kernel<2><<<grid, kMmaThreads, 0, a.st>>>(p);
-    return after_launch();
+    const int batch = tune_int("FP8B_GEMV_BATCH", 4);
+    if (a.M <= 8) {
+        if (batch == 4) return launch_ex(fp8_gemv_mma_kernel<1, 4>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+        if (batch == 1) return launch_ex(fp8_gemv_mma_kernel<1, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+        return launch_ex(fp8_gemv_mma_kernel<1, 2>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+    }
+    return launch_ex(fp8_gemv_mma_kernel<2, 4>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
 }
 
 }  // namespace fp8b

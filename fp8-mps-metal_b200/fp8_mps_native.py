@@ -53,6 +53,15 @@ def _to_device(t: torch.Tensor) -> torch.Tensor:
     return t if t.device.type == DEVICE_TYPE else t.to(_device())
 
 
+def set_static_weights(flag: bool) -> None:
+    """Promise (or withdraw the promise) that weight matrices passed as B are never written by work still
+    in flight on the stream.  The GEMV kernels then start streaming B before the preceding kernel has
+    finished (programmatic dependent launch), which overlaps consecutive decode GEMVs.  Off by default;
+    no reference counterpart."""
+    lib = _get_lib()
+    lib.set_option(lib.OPT_STATIC_WEIGHTS, 1 if flag else 0)
+
+
 def fp8_scaled_mm(A: torch.Tensor, B: torch.Tensor,
                   scale_a: torch.Tensor, scale_b: torch.Tensor) -> torch.Tensor:
     """

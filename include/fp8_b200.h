@@ -72,6 +72,23 @@ FP8B_API int fp8b_last_cuda_error(void);
  * reads it before/after the timed region to report `gpu_launches`. */
 FP8B_API uint64_t fp8b_launch_count(void);
 
+/*
+ * Library options (process-wide, may be changed between calls).
+ *   FP8B_OPT_PDL             1 (default): programmatic dependent launch may be used (it is used when
+ *                            FP8B_OPT_STATIC_WEIGHTS is on).  0: plain stream order always.
+ *   FP8B_OPT_STATIC_WEIGHTS  0 (default).  1: the caller promises that the B operand (the weight matrix) of
+ *                            fp8b_scaled_mm is never written by work still in flight on the stream.  The GEMV
+ *                            kernels then start streaming B BEFORE waiting for the predecessor (only A, the
+ *                            scales and the bias are read after the wait), which overlaps the ramp-up of one
+ *                            call with the drain of the previous one in a chain of decode GEMVs.
+ */
+typedef enum fp8b_option {
+    FP8B_OPT_PDL = 0,
+    FP8B_OPT_STATIC_WEIGHTS = 1
+} fp8b_option;
+FP8B_API int fp8b_set_option(int option, int value);
+FP8B_API int fp8b_get_option(int option);
+
 /* ---- casts ------------------------------------------------------------------------------ */
 
 /*

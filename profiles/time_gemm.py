@@ -11,6 +11,7 @@ for p in (os.path.join(ROOT, "fp8-mps-metal_b200"), os.path.join(ROOT, "tests"))
 import torch
 from _util import capi
 L = capi(); dev = torch.device("cuda", 0)
+L.fp8b_set_option(0, int(os.environ.get("PDL", "1"))); L.fp8b_set_option(1, int(os.environ.get("STATICW", "0")))
 M, K, N = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (4096, 3072, 12288)))
 algo = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 g = torch.Generator(device=dev).manual_seed(0)
@@ -39,5 +40,5 @@ e0.record()
 for _ in range(10): gr.replay()
 e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 1e3 / 40
-env = {k: v for k, v in os.environ.items() if k.startswith("FP8B_")}
+env = {k: v for k, v in os.environ.items() if k.startswith("FP8B_") or k in ("PDL", "STATICW")}
 print(f"{env} M{M} K{K} N{N} algo{algo}: {us:.2f} us  {2.0*M*N*K/us/1e6:.0f} TFLOP/s  {(M*K+N*K)/us/1e3:.0f} GB/s(in)")

@@ -1,0 +1,114 @@
+// Calibration microbenchmark: what can an SM kernel stream from HBM on this GPU?
+//   read-only (16 B / 32 B loads, several grid shapes) and copy, at 58.7 MB (the C2 weight matrix) and 2 GiB.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o membw membw.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+template <int U, bool NOALLOC>
+__global__ void __launch_bounds__(256) read_kernel(const uint4* __restrict__ in, size_t nvec, unsigned* out)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned acc = 0;
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+        uint4 w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            size_t v = v0 + u * stride;
+            if (v < nvec) {
+                if (NOALLOC) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(in + v));
+                else w[u] = in[v];
+            } else w[u] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += w[u].x ^ w[u].y ^ w[u].z ^ w[u].w;
+    }
+    if (acc == 0x12345678u) *out = acc;
+}
+
+// contiguous-per-CTA variant: each CTA owns a contiguous slab (like a row block)
+template <int U>
+__global__ void __launch_bounds__(256) read_slab_kernel(const uint4* __restrict__ in, size_t nvec, unsigned* out)
+{
+    size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    size_t b = (size_t)blockIdx.x * per, e = b + per < nvec ? b + per : nvec;
+    unsigned acc = 0;
+    for (size_t v0 = b + threadIdx.x; v0 < e; v0 += 256 * U) {
+        uint4 w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            size_t v = v0 + u * 256;
+            if (v < e) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[u].x), "=r"(w[u].y), "=r"(w[u].z), "=r"(w[u].w) : "l"(in + v));
+            else w[u] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += w[u].x ^ w[u].y ^ w[u].z ^ w[u].w;
+    }
+    if (acc == 0x12345678u) *out = acc;
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ outp, size_t nvec)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * U) {
+        uint4 w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { size_t v = v0 + u * stride; if (v < nvec) w[u] = in[v]; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { size_t v = v0 + u * stride; if (v < nvec) outp[v] = w[u]; }
+    }
+}
+
+template <typename F>
+static float time_us(F f, int reps)
+{
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) f(i);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) f(i);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    return ms * 1e3f / reps;
+}
+
+int main()
+{
+    const size_t small = 58720256, big = (size_t)2 << 30;
+    uint8_t *a, *b; unsigned* out;
+    cudaMalloc(&a, big); cudaMalloc(&b, big); cudaMalloc(&out, 4);
+    cudaMemset(a, 1, big); cudaMemset(b, 2, big);
+    const int nrot = 16;     // rotate 16 distinct 58.7 MB regions (> L2)
+    auto rd = [&](const char* name, auto kernel, int grid, size_t bytes) {
+        size_t nvec = bytes / 16;
+        float us = time_us([&](int i) {
+            const uint4* p = (const uint4*)(a + (bytes == small ? (size_t)(i % nrot) * small : 0));
+            kernel<<<grid, 256>>>(p, nvec, out); }, bytes == small ? 64 : 10);
+        printf("%-34s grid %5d  %8.1f MB  %8.2f us  %7.1f GB/s\n", name, grid, bytes / 1e6, us, bytes / us / 1e3);
+    };
+    for (size_t bytes : {small, big}) {
+        rd("read U4 noalloc", read_kernel<4, true>, 148 * 8, bytes);
+        rd("read U8 noalloc", read_kernel<8, true>, 148 * 8, bytes);
+        rd("read U8 noalloc", read_kernel<8, true>, 148 * 4, bytes);
+        rd("read U16 noalloc", read_kernel<16, true>, 148 * 4, bytes);
+        rd("read U8 default", read_kernel<8, false>, 148 * 8, bytes);
+        rd("read U4 noalloc", read_kernel<4, true>, 148 * 16, bytes);
+        rd("read slab U8", read_slab_kernel<8>, 148 * 4, bytes);
+        rd("read slab U8", read_slab_kernel<8>, 512, bytes);
+        rd("read slab U4", read_slab_kernel<4>, 4096, bytes);
+    }
+    for (size_t bytes : {small, big}) {
+        size_t nvec = bytes / 16;
+        for (int g : {148 * 4, 148 * 8, 148 * 16}) {
+            float us = time_us([&](int i) { copy_kernel<4><<<g, 256>>>((const uint4*)a, (uint4*)b, nvec); }, 10);
+            printf("%-34s grid %5d  %8.1f MB  %8.2f us  %7.1f GB/s (r+w)\n", "copy U4", g, bytes / 1e6, us, 2.0 * bytes / us / 1e3);
+        }
+        float us = time_us([&](int i) { cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice); }, 10);
+        printf("%-34s             %8.1f MB  %8.2f us  %7.1f GB/s (r+w)\n", "cudaMemcpyAsync D2D", bytes / 1e6, us, 2.0 * bytes / us / 1e3);
+    }
+    // empty-kernel launch cadence
+    float us = time_us([&](int i) { read_kernel<4, true><<<148, 256>>>((const uint4*)a, 0, out); }, 200);
+    printf("empty kernel back-to-back: %.2f us per launch\n", us);
+    return 0;
+}

@@ -34,6 +34,10 @@ def capi():
     L.fp8b_status_string.argtypes = [i32]
     L.fp8b_last_cuda_error.restype = i32
     L.fp8b_launch_count.restype = ctypes.c_uint64
+    L.fp8b_set_option.restype = i32
+    L.fp8b_set_option.argtypes = [i32, i32]
+    L.fp8b_get_option.restype = i32
+    L.fp8b_get_option.argtypes = [i32]
     L.fp8b_dequant_f16.restype = i32
     L.fp8b_dequant_f16.argtypes = [vp, vp, sz, vp, vp]
     L.fp8b_dequant.restype = i32
