@@ -45,8 +45,8 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kBRows = BN / CG;                         // B rows staged by one CTA
     static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (kStageBytes == 49152) ? 4 : (kStageBytes == 32768 ? 6 : 8);
-    static constexpr int kTmemCols = 2 * BN;                       // 512 or 256: a power of two >= 32
+    static constexpr int kStages = (kStageBytes > 32768) ? 4 : (kStageBytes > 24576 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;   // two accumulators; a power of two >= 32
     static constexpr int kBarBytes = 256;
     static constexpr int kEpiStageBytes = 4 * 8192;                // per epilogue warp: 32 rows x 256 B, XOR-swizzled
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;   // +1024: manual alignment
@@ -458,7 +458,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const int ppc = is_f32 ? 8 : 4;                      // 16-byte pieces per chunk per row
                     const int cg = (c0 >> 5) & (cpg - 1);                // chunk index inside its group
                     const int ng0 = n0 - cg * 32;                        // first column of the group
-                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4);   // warp-uniform
+                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4) &&
+                                        ((c0 - cg * 32) + cpg * 32 <= (col_part + 1) * kColsPerWarp);   // warp-uniform; whole group inside the tile
                     if (staged) {
                         const uint32_t st_base = stage_base + (uint32_t)(warp - 2) * 8192u + (uint32_t)lane * 256u;
 #pragma unroll
@@ -607,22 +608,34 @@ int launch_gemm_tcgen05(const MMArgs& a)
     if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
     // Tile choice.  Prefer CTA pairs (256-row tiles) whenever M and N are large enough for them,
     // 256-wide when that still leaves >= ~2 waves of tiles, else 128-wide (finer tail).
-    // FP8B_GEMM_CFG forces one: 1 = 128x256 1-CTA, 2 = 128x128 1-CTA, 3 = 256x256 pair, 4 = 256x128 pair.
+    // FP8B_GEMM_CFG forces one: 1 = 128x256 1-CTA, 2 = 128x128 1-CTA, 3 = 256x256 pair, 4 = 256x128 pair,
+    // 5 = 256x192 pair.
     const int sms = device_info().sm_count;
     int cfg = tune_int("FP8B_GEMM_CFG", 0);
     if (cfg == 0) {
-        const long t_pair256 = (long)((a.M + 255) / 256) * ((a.N + 255) / 256);
-        const long t_pair128 = (long)((a.M + 255) / 256) * ((a.N + 127) / 128);
-        const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
-        if (a.M > 128 && a.N > 128 && t_pair256 >= 2L * (sms / 2)) cfg = 3;
-        else if (a.M > 128 && a.N >= 128 && t_pair128 >= (sms / 2)) cfg = 4;
-        else if (a.N > 128 && t_256 >= 2L * sms) cfg = 1;
-        else cfg = 2;
+        if (a.M > 128 && a.N > 128) {
+            // CTA pairs.  Pick the tile width minimising rounds x time-per-tile; the per-tile times are the
+            // measured ones for K = 3072 (256: 10.5 us, 192: 9.3 us, 128: 8.65 us -- L2->SM traffic per tile,
+            // not MMA time, dominates, so narrow tiles are barely cheaper) and only their ratios matter.
+            const long mt = (a.M + 255) / 256;
+            const int pairs = sms / 2;
+            const double cost256 = 10.5 * (double)((mt * ((a.N + 255) / 256) + pairs - 1) / pairs);
+            const double cost192 = 9.3 * (double)((mt * ((a.N + 191) / 192) + pairs - 1) / pairs);
+            const double cost128 = 8.65 * (double)((mt * ((a.N + 127) / 128) + pairs - 1) / pairs);
+            cfg = 3;
+            double best = cost256;
+            if (cost192 < best) { best = cost192; cfg = 5; }
+            if (cost128 < best) { best = cost128; cfg = 4; }
+        } else {
+            const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
+            cfg = (a.N > 128 && t_256 >= 2L * sms) ? 1 : 2;
+        }
     }
     switch (cfg) {
         case 1: return launch_tcgen05_cfg<256, 1>(a);
         case 3: return launch_tcgen05_cfg<256, 2>(a);
         case 4: return launch_tcgen05_cfg<128, 2>(a);
+        case 5: return launch_tcgen05_cfg<192, 2>(a);
         default: return launch_tcgen05_cfg<128, 1>(a);
     }
 }

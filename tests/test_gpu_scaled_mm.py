@@ -217,7 +217,7 @@ def test_tcgen05_gemm(M, K, N, odt, kw):
     _run_case(M, K, N, odt, ALGO_TCGEN05, seed=M + K + N, tol=tol, **kw)
 
 
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,K,N,odt,kw", [
     (256, 512, 384, torch.bfloat16, {"per_row_a": True, "per_row_b": True}),
     (200, 336, 1000, None, {"bias_dtype": torch.float32, "scale_result": True}),      # ragged M, N, K
@@ -227,7 +227,7 @@ def test_tcgen05_gemm(M, K, N, odt, kw):
 ])
 def test_tcgen05_all_tile_configs(monkeypatch, cfg, M, K, N, odt, kw):
     """FP8B_GEMM_CFG: 1 = 128x256 tile, one CTA; 2 = 128x128, one CTA; 3 = 256x256, CTA pair
-    (cta_group::2); 4 = 256x128, CTA pair.  Every configuration must serve every shape."""
+    (cta_group::2); 4 = 256x128, CTA pair; 5 = 256x192, CTA pair.  Every configuration must serve every shape."""
     monkeypatch.setenv("FP8B_GEMM_CFG", str(cfg))
     tol = 1e-4 if odt is None else None
     _run_case(M, K, N, odt, ALGO_TCGEN05, seed=cfg + M + N, tol=tol, **kw)
