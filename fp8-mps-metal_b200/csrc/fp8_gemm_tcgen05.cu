@@ -8,21 +8,22 @@
 // passes (fp8_mps_patch.py:95-104).  One launch here.
 //
 // Structure (persistent, warp-specialised, one CTA per SM):
-//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 128 B A tile and a BN x 128 B
+//   warp 4      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 128 B A tile and a BN x 128 B
 //               B tile per k-block into a STAGES-deep 128B-swizzled shared-memory ring (mbarrier
 //               complete_tx).  The reference's (N,K) weight layout is already the K-major form
 //               tcgen05 wants, so neither operand is transposed.  TMA zero-fills out-of-range rows and
 //               the K tail; 0x00 decodes to 0, so edges need no special code.
-//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f8f6f4 (M=128, N=BN, K=32),
+//   warp 5      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f8f6f4 (M=128, N=BN, K=32),
 //               four per k-block; tcgen05.commit releases each smem slot and finally publishes the
 //               accumulator.
-//   warps 2-5   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
+//   warps 0-3   epilogue: tcgen05.ld (32 lanes x 32 columns per warp per step) -> ((acc*sa)*sb)+bias,
 //               *scale_result -> out dtype -> 16-byte global stores.  Two accumulators of BN columns
 //               live in TMEM (2*BN <= 512 columns) so the epilogue of tile i overlaps the main loop
 //               of tile i+1.
 // NaN bytes (0x7F/0xFF) make the hardware accumulator NaN where the reference decodes 0
 // (metal:21); the epilogue recomputes exactly those outputs with the masked scalar loop.
 #include <cuda.h>
+#include <cstdio>
 #include <mutex>
 #include "fp8_mm.cuh"
 
@@ -35,7 +36,13 @@ constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
 // tile's columns.  Measured on C4 (256x256 pair tiles): 4 warps 113.1 us, 8 warps 119.3 us -> 4.
 constexpr int kNumEpiWarps = 4;   // the staging buffer below is sized for 4
 constexpr int kEpiColSplits = kNumEpiWarps / 4;
-constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;   // warp 0 TMA, warp 1 MMA, the rest epilogue
+constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;
+// Warp roles.  The epilogue takes the LOW warp ids and the two single-thread roles the HIGH ones: the warp
+// scheduler favours higher warp ids among eligible warps, and the MMA issuer / TMA producer are latency-critical
+// (with the roles the other way round the epilogue's ALU stream delayed MMA issue: 14.2K vs 12.4K cycles per tile).
+constexpr int kWarpEpi0 = 0;                    // warps 0..kNumEpiWarps-1: epilogue (TMEM lane quarter = warp % 4)
+constexpr int kWarpTma = kNumEpiWarps;          // TMA producer
+constexpr int kWarpMma = kNumEpiWarps + 1;      // MMA issuer
 
 // CG = CTA-group size.  CG == 2: two CTAs of a cluster (an SM pair) compute one 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, so the
@@ -60,6 +67,7 @@ struct GemmParams {
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
     int store_mc;                            // C is an NVSwitch multicast address: store with multimem.st
+    long long* dbg;                          // FP8B_GEMM_DEBUG & 16: per-tile clock64 stamps of CTA 0 (profiling only)
     int debug;                               // FP8B_GEMM_DEBUG profiling knob: 1 = no stores, 2 = drain TMEM only
 };
 
@@ -258,17 +266,17 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps * CG); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
-    if (warp == 2) {
+    if (warp == kWarpEpi0) {
         if (CG == 2) { tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols); tmem_relinquish_2sm(); }
         else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), Cfg::kTmemCols); tmem_relinquish(); }
     }
@@ -280,17 +288,21 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;
 
-    if (warp == 0) {
+    if (warp == kWarpTma) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            int issued = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const int m_idx = (tile % p.num_m_blocks) * kTileM + (int)cta_rank * kBM;
                 const int n_idx = (tile / p.num_m_blocks) * BN + (int)cta_rank * Cfg::kBRows;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-                    if (CG == 2) {
+                    if ((p.debug & 32) && issued >= Cfg::kStages) {
+                        // profiling only: no TMA traffic after the ring is primed (results are garbage)
+                        if (is_leader) mbar_arrive(full_bar(stage));
+                    } else if (CG == 2) {
                         // both CTAs load their halves; all bytes are accounted on the leader's barrier
                         if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
                         tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
@@ -300,19 +312,22 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
                         tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
                     }
+                    ++issued;
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
         if (lane == 0 && is_leader) {
             constexpr uint32_t idesc = make_idesc(kTileM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const long long t_m0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);           // epilogue has drained this accumulator
                 tc_fence_after();
+                const long long t_m1 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
@@ -331,13 +346,17 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
                 if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
+                if (p.dbg && blockIdx.x == 0) {
+                    const int ti = (tile - worker) / num_workers;
+                    if (ti < 64) { p.dbg[ti * 8 + 0] = t_m0; p.dbg[ti * 8 + 1] = t_m1; p.dbg[ti * 8 + 2] = clock64(); }
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 0..3) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
-        const int col_part = (warp - 2) >> 2;         // which slice of the tile's columns this warp drains
+        const int col_part = (warp - kWarpEpi0) >> 2;         // which slice of the tile's columns this warp drains
         constexpr int kColsPerWarp = BN / kEpiColSplits;
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
@@ -350,8 +369,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
             const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
+            const long long t_e0 = (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            const long long t_e1 = (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = col_part * kColsPerWarp; c0 < (col_part + 1) * kColsPerWarp; c0 += 32) {
@@ -461,7 +482,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4) &&
                                         ((c0 - cg * 32) + cpg * 32 <= (col_part + 1) * kColsPerWarp);   // warp-uniform; whole group inside the tile
                     if (staged) {
-                        const uint32_t st_base = stage_base + (uint32_t)(warp - 2) * 8192u + (uint32_t)lane * 256u;
+                        const uint32_t st_base = stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u + (uint32_t)lane * 256u;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (j < ppc) {
@@ -479,7 +500,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 const int rr = 2 * i + (lane >> 4);
                                 const int gm = m_idx + q * 32 + rr;
                                 uint32_t a0, a1, a2, a3;
-                                lds_v4(stage_base + (uint32_t)(warp - 2) * 8192u + (uint32_t)rr * 256u +
+                                lds_v4(stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u + (uint32_t)rr * 256u +
                                        (uint32_t)((piece ^ (rr & 15)) * 16), a0, a1, a2, a3);
                                 if (gm < p.M) stg_v4(cbase + (size_t)gm * e.ldc * esz, a0, a1, a2, a3, p.store_mc);
                             }
@@ -500,6 +521,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
             }
+            if (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) {
+                const int ti = (tile - worker) / num_workers;
+                if (ti < 64) { p.dbg[ti * 8 + 4] = t_e0; p.dbg[ti * 8 + 5] = t_e1; p.dbg[ti * 8 + 6] = clock64(); }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -507,7 +532,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_before();
     if (CG == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while its peer still signals it
     else __syncthreads();
-    if (warp == 2) {
+    if (warp == kWarpEpi0) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
@@ -581,6 +606,13 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
     p.debug = tune_int("FP8B_GEMM_DEBUG", 0);
     p.store_mc = a.store_mc;
+    p.dbg = nullptr;
+    if (p.debug & 16) {                      // profiling only: allocates and synchronises
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 64 * 8 * sizeof(long long));
+        cudaMemset(dbuf, 0, 64 * 8 * sizeof(long long));
+        p.dbg = dbuf;
+    }
     // multimem.st has no sub-word form: the multicast mode needs every chunk on the 16-byte path
     if (a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
@@ -600,6 +632,16 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     cfg.numAttrs = CG > 1 ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG>, tmap_a, tmap_b, p);
     if (e != cudaSuccess) return cuda_fail(e);
+    if (p.dbg) {
+        long long h[64 * 8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("tile | mma: wait_tempty  issue+run | epi: wait_tfull  drain+store | epi_end - mma_end\n");
+        for (int t = 0; t < 64 && h[t * 8 + 2]; ++t)
+            printf("%4d | %8lld %8lld | %8lld %8lld | %8lld   (mma start %lld)\n", t, h[t * 8 + 1] - h[t * 8 + 0],
+                   h[t * 8 + 2] - h[t * 8 + 1], h[t * 8 + 5] - h[t * 8 + 4], h[t * 8 + 6] - h[t * 8 + 5],
+                   h[t * 8 + 6] - h[t * 8 + 2], h[t * 8 + 0] - h[0]);
+    }
     return after_launch();
 }
 

@@ -1,0 +1,15 @@
+import ctypes, os, sys
+ROOT=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0,ROOT+'/fp8-mps-metal_b200'); sys.path.insert(0,ROOT+'/tests')
+import torch
+from _util import capi
+L=capi(); dev=torch.device('cuda',0)
+M,K,N=4096,3072,12288
+g=torch.Generator(device=dev).manual_seed(0)
+A=torch.randint(0,120,(M,K),dtype=torch.uint8,device=dev,generator=g); B=torch.randint(0,120,(N,K),dtype=torch.uint8,device=dev,generator=g)
+C=torch.empty(M,N,dtype=torch.bfloat16,device=dev); one=torch.full((1,),0.01,device=dev)
+P=lambda t: ctypes.c_void_p(t.data_ptr())
+for i in range(3):
+    if i==2: os.environ['FP8B_GEMM_DEBUG']=str(16+int(os.environ.get('DBG_EXTRA','0')))
+    rc=L.fp8b_scaled_mm(P(A),P(B),P(C),2,M,N,K,N,P(one),1,P(one),1,None,0,None,None,0,2,None); assert rc==0
+torch.cuda.synchronize()
