@@ -610,7 +610,7 @@ def main():
                 sh["layouts"] = {"allgather_rank_major": "[world, M, N/world], no re-layout pass",
                                  "allgather_row_major": "(M, N) contiguous, one extra device pass",
                                  "multicast_fused": "(M, N) row-major on every rank, written by the GEMM epilogue through "
-                                                    "the NVSwitch multicast mapping; two symmetric-memory barriers per call"}
+                                                    "the NVSwitch multicast mapping; double-buffered, one symmetric-memory barrier per call"}
                 sub[key]["sharded"] = sh
             del bufs
         except Exception as e:
