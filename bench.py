@@ -71,6 +71,23 @@ def load_peaks():
     return dict(hbm=FALLBACK_HBM_GBS, bf16=FALLBACK_BF16_TFLOPS, bf16_sustained=1400.0, source="fallback")
 
 
+def profile_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed ncu capture
+    profiles/r1_<name>_raw.csv (one `ncu --set full` capture of the same kernel and shape), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", f"r1_{name}_raw.csv")
+    if not os.path.exists(path):
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    found = 0
+    for row in csv.reader(open(path)):
+        if len(row) == 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(row[1].replace(",", "")) * mult.get(row[2], 1.0)
+            found += 1
+    return int(tot) if found == 2 else None
+
+
 # --------------------------------------------------------------------------- clocks
 
 class ClockSampler:
@@ -377,33 +394,53 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
     offs = [0]
     for s in sizes:
         offs.append(offs[-1] + s)
-    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
 
-    def quant():
-        s_ = st()
+    def sweep(call, n_streams):
+        """One launch per tensor.  n_streams > 1: independent tensors are issued round-robin on forked
+        streams (joined back before the step ends), so the drain of one launch overlaps the ramp of the next."""
+        cur = torch.cuda.current_stream()
+        if n_streams <= 1:
+            sp = ctypes.c_void_p(cur.cuda_stream)
+            for i, n in enumerate(sizes):
+                call(i, n, sp)
+            return
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for s_ in side[:n_streams]:
+            s_.wait_event(fork)
         for i, n in enumerate(sizes):
-            rc = L.fp8b_encode(ctypes.c_void_p(src.data_ptr() + 2 * offs[i]), 2, ctypes.c_void_p(q.data_ptr() + offs[i]),
-                               n, None, s_)
-            assert rc == 0
+            call(i, n, ctypes.c_void_p(side[i % n_streams].cuda_stream))
+        for s_ in side[:n_streams]:
+            j = torch.cuda.Event()
+            j.record(s_)
+            cur.wait_event(j)
 
-    def dequant():
-        s_ = st()
-        for i, n in enumerate(sizes):
-            rc = L.fp8b_dequant_f16(ctypes.c_void_p(q.data_ptr() + offs[i]), ctypes.c_void_p(h.data_ptr() + 2 * offs[i]),
-                                    n, None, s_)
-            assert rc == 0
+    def quant_one(i, n, sp):
+        rc = L.fp8b_encode(ctypes.c_void_p(src.data_ptr() + 2 * offs[i]), 2, ctypes.c_void_p(q.data_ptr() + offs[i]), n, None, sp)
+        assert rc == 0
+
+    def dequant_one(i, n, sp):
+        rc = L.fp8b_dequant_f16(ctypes.c_void_p(q.data_ptr() + offs[i]), ctypes.c_void_p(h.data_ptr() + 2 * offs[i]), n, None, sp)
+        assert rc == 0
 
     out = {}
-    for name, fn in (("quantize_bf16_to_fp8", quant), ("dequant_fp8_to_fp16", dequant)):
-        ms, launches, _, _ = time_graph(torch, fn, max(3, min(steps, 5)), max(warmup, 3))
-        k = max(3, min(steps, 5))
-        ms_sweep = ms / k
-        gbs = 3.0 * total / (ms_sweep * 1e-3) / 1e9
+    k = max(3, min(steps, 5))
+    for name, one in (("quantize_bf16_to_fp8", quant_one), ("dequant_fp8_to_fp16", dequant_one)):
+        res = {}
+        for ns in (1, 4):
+            ms, launches, _, _ = time_graph(torch, lambda: sweep(one, ns), k, max(warmup, 3))
+            ms_sweep = ms / k
+            res[ns] = (ms_sweep, 3.0 * total / (ms_sweep * 1e-3) / 1e9, launches)
+        ms_sweep, gbs, launches = res[1]
         out[name] = {"ms_per_sweep": round(ms_sweep, 3), "value": round(gbs, 1), "unit": "GB/s", "elements": total,
                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                   "frac": round(gbs / peaks["hbm"], 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
                                   "traffic": None, "peak_source": peaks["source"]},
-                     "launches_per_sweep": launches, "l2": "35.5 GB working set per sweep >> L2"}
+                     "launches_per_sweep": launches, "l2": "35.5 GB working set per sweep >> L2",
+                     "four_streams": {"ms_per_sweep": round(res[4][0], 3), "value": round(res[4][1], 1), "unit": "GB/s",
+                                      "frac": round(res[4][1] / peaks["hbm"], 4),
+                                      "note": "same per-tensor launches issued round-robin on 4 forked streams"}}
     # spot parity on the last tensor (bit-exact vs the C oracle on a strided sample)
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -542,7 +579,7 @@ def main():
                    "algorithmic_bytes_per_call": C2_BYTES, "parallelism": "replicas" if n_gpus > 1 else "single-gpu",
                    "arith": "e4m3 operands, exact fp16 products, fp32 accumulation (FHFMA)"},
         "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": round(per_gpu / peaks["hbm"], 4), "traffic": None,
+                     "frac": round(per_gpu / peaks["hbm"], 4), "traffic": profile_traffic("gemv"),
                      "frac_of_nominal_8000": round(per_gpu / 8000.0, 4), "us_per_launch": round(us_per_call, 3),
                      "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json)",
                      "kernel": "fp8_gemv_kernel<1,4>",
@@ -564,6 +601,7 @@ def main():
                                                                peaks, args.steps, args.warmup, rotation=32)
             sub["C3_gemv_M4_K4096_N4096_bias_bf16"] = bench_gemv_cfg(torch, L, C3, C3_BYTES, torch.bfloat16, True, gen,
                                                                      dev, peaks, args.steps, args.warmup, rotation=32)
+            sub["C3_gemv_M4_K4096_N4096_bias_bf16"]["roofline"]["traffic"] = profile_traffic("gemv4")
         except Exception as e:
             sub["gemv_error"] = repr(e)
         try:
@@ -575,6 +613,8 @@ def main():
             res["clocks"] = s2.summary(tg0, time.perf_counter())
             s2.stop()
             key = "C4_gemm_M4096_K3072_N12288_bf16" + (f"_shard{n_gpus}" if n_gpus > 1 else "")
+            if n_gpus == 1:
+                res["roofline"]["traffic"] = profile_traffic("gemm")
             sub[key] = res
             if dist is not None:
                 from fp8_sharded import ShardedScaledMM

@@ -215,6 +215,23 @@ void fp8_scaled_mm_multicast(torch::Tensor A, torch::Tensor B, torch::Tensor sca
     check_status(rc, "fp8b_scaled_mm_multicast");
 }
 
+// per-row fp8_quantize of a 2-D tensor: returns (uint8 (rows, cols), inv_scale float32 [rows])
+std::tuple<torch::Tensor, torch::Tensor> fp8_quantize_rowwise(torch::Tensor input)
+{
+    TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
+    TORCH_CHECK(input.dim() == 2, "input must be 2-D (rows, cols)");
+    c10::cuda::CUDAGuard guard(input.device());
+    torch::Tensor in = input.contiguous();
+    if (in.scalar_type() != at::kFloat && in.scalar_type() != at::kHalf && in.scalar_type() != at::kBFloat16)
+        in = in.to(torch::kFloat32);
+    torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(torch::kUInt8).device(in.device()));
+    torch::Tensor inv = torch::empty({in.size(0)}, torch::TensorOptions().dtype(torch::kFloat32).device(in.device()));
+    check_status(fp8b_quantize_rows(in.data_ptr(), to_fp8b_dtype(in.scalar_type()), (int)in.size(0), (size_t)in.size(1),
+                                    static_cast<uint8_t*>(out.data_ptr()), inv.data_ptr<float>(), current_stream()),
+                 "fp8b_quantize_rows");
+    return std::make_tuple(out, inv);
+}
+
 int64_t select_algo(torch::Tensor A, torch::Tensor B, at::ScalarType out_dtype)
 {
     return fp8b_scaled_mm_select(u8_ptr(A), u8_ptr(B), nullptr, to_fp8b_dtype(out_dtype), (int)A.size(0), (int)B.size(0),
@@ -231,6 +248,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("fp8_dequantize", &fp8_dequantize, "FP8 to float16 dequantization on the GPU",
           py::arg("input"), py::arg("scale"));
     m.def("fp8_quantize", &fp8_quantize, "Float to FP8 quantization on the GPU", py::arg("input"));
+    m.def("fp8_quantize_rowwise", &fp8_quantize_rowwise, "Per-row float to FP8 quantization", py::arg("input"));
     m.def("fp8_encode", &fp8_encode, "Float to FP8 encoding without scaling", py::arg("input"));
     m.def("fp8_dequantize_to", &fp8_dequantize_to, "FP8 to float32/float16/bfloat16 exact cast",
           py::arg("input"), py::arg("dtype"));

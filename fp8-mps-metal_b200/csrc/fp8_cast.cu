@@ -310,6 +310,66 @@ __global__ void amax_finalize_kernel(uint32_t* amax_bits, float* scale_out, floa
     *amax_bits = 0u;
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-wise (per-channel) quantise: fp8_quantize (fp8_mps_native.py:158-190) applied to every row of a
+// (rows, cols) matrix in ONE launch -- amax, double-precision scale and fused multiply+encode per row --
+// producing the per-row inverse scales that `_scaled_mm` takes as a length-M / length-N scale.
+// One CTA per row; the second pass re-reads the row from L2.
+template <int IN>
+__global__ void __launch_bounds__(kCastThreads)
+quantize_rows_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, float* __restrict__ inv_scale,
+                     size_t cols, int vec_ok)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    constexpr int ESZ = (IN == FP8B_F32) ? 4 : 2;
+    const size_t row = blockIdx.x;
+    const uint8_t* rin = reinterpret_cast<const uint8_t*>(in) + row * cols * ESZ;
+    uint8_t* rout = out + row * cols;
+    const size_t nvec = vec_ok ? cols / EPV : 0;
+    uint32_t m = 0;
+    for (size_t v = threadIdx.x; v < nvec; v += kCastThreads) {
+        const uint4 w = *reinterpret_cast<const uint4*>(rin + v * 16);
+        const uint32_t* p = &w.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (IN == FP8B_F32) m = max(m, p[j] & 0x7FFFFFFFu);
+            else if (IN == FP8B_BF16) { m = max(m, (p[j] << 16) & 0x7FFFFFFFu); m = max(m, p[j] & 0x7FFF0000u); }
+            else {
+                float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
+                m = max(m, __float_as_uint(t.x) & 0x7FFFFFFFu);
+                m = max(m, __float_as_uint(t.y) & 0x7FFFFFFFu);
+            }
+        }
+    }
+    for (size_t i = nvec * EPV + threadIdx.x; i < cols; i += kCastThreads)
+        m = max(m, __float_as_uint(load_wide_scalar<IN>(rin, i)) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    __shared__ uint32_t sm[kCastThreads / 32];
+    __shared__ float s_scale;
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t mm = 0;
+        for (int i = 0; i < kCastThreads / 32; ++i) mm = max(mm, sm[i]);
+        const float amax = __uint_as_float(mm);
+        const double scale = (amax > 0.0f) ? 448.0 / (double)amax : 1.0;     // native.py:175-176, in double
+        s_scale = (float)scale;
+        inv_scale[row] = (float)(1.0 / scale);                                 // native.py:189
+    }
+    __syncthreads();
+    const float s = s_scale;
+    for (size_t v = threadIdx.x; v < nvec; v += kCastThreads) {
+        const uint4 w = *reinterpret_cast<const uint4*>(rin + v * 16);
+        uint32_t o0, o1;
+        encode_vec<IN, true>(w, s, o0, o1);
+        if (IN == FP8B_F32) *reinterpret_cast<uint32_t*>(rout + v * 4) = o0;
+        else *reinterpret_cast<uint2*>(rout + v * 8) = make_uint2(o0, o1);
+    }
+    for (size_t i = nvec * EPV + threadIdx.x; i < cols; i += kCastThreads)
+        rout[i] = enc1_f32(__fmul_rn(load_wide_scalar<IN>(rin, i), s));
+}
+
 static int cast_grid(size_t work_items) {
     const DeviceInfo& di = device_info();
     size_t want = (work_items + kCastThreads - 1) / kCastThreads;
@@ -418,5 +478,23 @@ extern "C" int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* sc
         if (rc != FP8B_OK) return rc;
     }
     amax_finalize_kernel<<<1, 1, 0, st>>>(scratch, scale_out, inv_scale_out);
+    return after_launch();
+}
+
+extern "C" int fp8b_quantize_rows(const void* in, int in_dtype, int rows, size_t cols, uint8_t* out,
+                                  float* inv_scale_out, void* stream)
+{
+    if (!valid_dtype(in_dtype) || rows < 0) return FP8B_ERR_INVALID;
+    if (rows == 0) return FP8B_OK;
+    if (!inv_scale_out || (cols != 0 && (!in || !out))) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype_size(in_dtype);
+    const size_t epv = 16 / esz;
+    // vector path: every row start 16-byte aligned on the wide side and epv-byte aligned on the fp8 side
+    const int vec_ok = aligned(in, 16) && aligned(out, epv) && ((cols * esz) % 16 == 0) ? 1 : 0;
+    if (in_dtype == FP8B_F32) quantize_rows_kernel<FP8B_F32><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
+    else if (in_dtype == FP8B_F16) quantize_rows_kernel<FP8B_F16><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
+    else quantize_rows_kernel<FP8B_BF16><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
     return after_launch();
 }

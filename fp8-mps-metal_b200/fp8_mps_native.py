@@ -150,6 +150,19 @@ def fp8_quantize(input: torch.Tensor):
     return lib.fp8_quantize(inp)
 
 
+def fp8_quantize_rowwise(input: torch.Tensor):
+    """
+    Per-row (per-channel) `fp8_quantize`: the reference's amax -> 448/amax -> encode arithmetic
+    (fp8_mps_native.py:158-190) applied to each row of a 2-D tensor in one launch.
+
+    Returns: (uint8 (rows, cols), inverse scales float32 [rows]) -- the second is directly usable as a
+    per-row ``scale_a`` / ``scale_b`` of ``fp8_scaled_mm`` (the reference kernels' scale_mode 1,
+    fp8_matmul.metal:144-145, which the reference itself never feeds).
+    """
+    lib = _get_lib()
+    return lib.fp8_quantize_rowwise(_to_device(input))
+
+
 def fp8_scaled_mm_auto(A: torch.Tensor, B: torch.Tensor,
                        scale_a: torch.Tensor, scale_b: torch.Tensor) -> torch.Tensor:
     """Auto-select the matmul kernel from the shape (reference: fp8_mps_native.py:193-210):

@@ -126,6 +126,17 @@ FP8B_API int fp8b_encode(const void* in, int in_dtype, uint8_t* out, size_t n, c
 FP8B_API int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* scale_out, float* inv_scale_out,
                     uint32_t* scratch, void* stream);
 
+/*
+ * Row-wise (per-channel) quantise: the fp8_quantize arithmetic (fp8_mps_native.py:158-190) applied to each
+ * row of a contiguous (rows, cols) matrix in one launch:
+ *     amax_r = max_j |f32(in[r,j])|;  scale_r = amax_r > 0 ? 448.0/amax_r : 1.0 (double)
+ *     out[r,j] = enc( f32(in[r,j]) * (float)scale_r );   inv_scale_out[r] = (float)(1.0/scale_r)
+ * inv_scale_out (device float[rows]) is what fp8b_scaled_mm takes as a per-row scale_a / scale_b.
+ * (The reference only quantises per tensor; its kernels accept per-row scales, fp8_matmul.metal:144-145.)
+ */
+FP8B_API int fp8b_quantize_rows(const void* in, int in_dtype, int rows, size_t cols, uint8_t* out,
+                       float* inv_scale_out, void* stream);
+
 /* ---- scaled matmul ---------------------------------------------------------------------- */
 
 /*

@@ -46,6 +46,8 @@ def capi():
     L.fp8b_encode.argtypes = [vp, i32, vp, sz, vp, vp]
     L.fp8b_amax_scale.restype = i32
     L.fp8b_amax_scale.argtypes = [vp, i32, sz, vp, vp, vp, vp]
+    L.fp8b_quantize_rows.restype = i32
+    L.fp8b_quantize_rows.argtypes = [vp, i32, i32, sz, vp, vp, vp]
     L.fp8b_scaled_mm.restype = i32
     L.fp8b_scaled_mm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp, vp, sz, i32, vp]
     L.fp8b_scaled_mm_multicast.restype = i32

@@ -165,6 +165,26 @@ def test_quantize_golden_and_random(golden):
     assert (d.cpu().float() - x).abs().max().item() < 50.0
 
 
+@pytest.mark.parametrize("rows,cols,dtype", [(7, 1000, torch.float32), (64, 4096, torch.bfloat16), (3, 17, torch.float16),
+                                             (12288, 3072, torch.bfloat16), (5, 8, torch.float32), (1, 1, torch.float32)])
+def test_quantize_rowwise(rows, cols, dtype):
+    """Per-row quantise == the reference's fp8_quantize arithmetic applied row by row (oracle), bit for bit,
+    and its inverse scales feed _scaled_mm as per-row scales."""
+    import fp8_mps_native
+    g = torch.Generator().manual_seed(rows * 31 + cols)
+    x = (torch.randn(rows, cols, generator=g) * torch.rand(rows, 1, generator=g) * 10).to(dtype)
+    if rows > 2:
+        x[1].zero_()                                               # amax == 0 -> scale 1.0 (native.py:176)
+    q, inv = fp8_mps_native.fp8_quantize_rowwise(x.to(DEV))
+    assert q.shape == (rows, cols) and q.dtype == torch.uint8 and inv.shape == (rows,) and inv.dtype == torch.float32
+    qn, invn = q.cpu().numpy(), inv.cpu().numpy()
+    check_rows = range(rows) if rows <= 64 else range(0, rows, 97)
+    for r in check_rows:
+        rq, rinv = o.fp8_quantize(x[r].float().numpy())
+        assert np.array_equal(qn[r], rq), r
+        assert invn[r].view(np.uint32) == rinv.view(np.uint32)[0], r
+
+
 def test_full_size_properties():
     """BASELINE config 5 scale (one FLUX linear, 21504x3072 = 66 M elements, and a 1 Gi-element sweep
     of raw bytes): size-independent properties instead of an element-wise CPU oracle."""
