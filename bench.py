@@ -520,6 +520,30 @@ def main():
     finally:
         L.fp8b_set_option(1, 0)
     ms_static = max_over_ranks(torch, dist, ms_static)
+
+    # variant: the same 128 independent calls issued round-robin on 4 forked streams (each with its own output)
+    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    outs4 = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+
+    def step_streams():
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for s_ in side:
+            s_.wait_event(fork)
+        i = 0
+        for _ in range(PASSES):
+            for w, sc in zip(Ws, inv_ws):
+                with torch.cuda.stream(side[i % 4]):
+                    _mm(L, torch, x, w, outs4[i % 4], bf16, inv_x, sc)
+                i += 1
+        for s_ in side:
+            j = torch.cuda.Event()
+            j.record(s_)
+            cur.wait_event(j)
+
+    ms_streams, _, _, _ = time_graph(torch, step_streams, args.steps, args.warmup, dist)
+    ms_streams = max_over_ranks(torch, dist, ms_streams)
     calls = ROTATION * PASSES
     ms_per_step = ms / args.steps
     us_per_call = ms_per_step * 1e3 / calls
@@ -560,7 +584,32 @@ def main():
         e2e_launches = L.fp8b_launch_count() - n0
         e2e_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1))
         e2e_val = n_gpus * C2_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        # second reading of "host buffers": the plug-in's deployment shape -- FP8 weights were moved to the GPU once
+        # (fp8_mps_patch scenario 1), only the activation comes from / the result goes to the host every step
+        w8 = Ws[0].view(torch.float8_e4m3fn).t()
+
+        def e2e_step_resident():
+            dx.copy_(hx, non_blocking=True)
+            y = torch._scaled_mm(dx.view(torch.float8_e4m3fn), w8, sa_d, sb_d, None, None, torch.bfloat16)
+            hout.copy_(y, non_blocking=True)
+
+        for _ in range(max(args.warmup, 3)):
+            e2e_step_resident()
+        torch.cuda.synchronize()
+        r0 = torch.cuda.Event(enable_timing=True)
+        r1 = torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(e2e_steps * 8):
+            e2e_step_resident()
+        r1.record()
+        torch.cuda.synchronize()
+        res_ms = max_over_ranks(torch, dist, r0.elapsed_time(r1)) / (e2e_steps * 8)
         e2e = {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": int(hx.numel() + hW.numel()),
+               "resident_weights": {"value": round(n_gpus * C2_BYTES / (res_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                                    "ms_per_step": round(res_ms, 4), "h2d_bytes_per_step": int(hx.numel()),
+                                    "d2h_bytes_per_step": int(hout.numel() * 2),
+                                    "note": "weights already on the GPU (moved once, as the plug-in does); x copied in and y "
+                                            "copied out every step through the patched torch._scaled_mm; L2-warm (one weight)"},
                "d2h_bytes_per_step": int(hout.numel() * 2), "ms_per_step": round(e2e_ms / e2e_steps, 4),
                "steps": e2e_steps, "call": "torch._scaled_mm after fp8_mps_patch.install(); one GEMV per step; "
                "x and W copied from pinned host memory and the result read back every step",
@@ -588,6 +637,10 @@ def main():
         "static_weights_pdl": {"value": round(n_gpus * C2_BYTES * calls / (ms_static / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
                                "us_per_launch": round(ms_static / args.steps * 1e3 / calls, 3),
                                "note": "opt-in FP8B_OPT_STATIC_WEIGHTS=1: consecutive GEMVs overlap via programmatic dependent launch"},
+        "four_streams": {"value": round(n_gpus * C2_BYTES * calls / (ms_streams / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
+                         "frac": round(C2_BYTES * calls / (ms_streams / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
+                         "note": "the same 128 independent calls issued round-robin on 4 forked streams inside the graph: "
+                                 "ramp-up and drain of neighbouring launches overlap (not the headline: a decode chain is serial)"},
         "e2e": e2e,
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
