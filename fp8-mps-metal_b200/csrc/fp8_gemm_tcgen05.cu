@@ -475,33 +475,37 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     // XOR-swizzled shared-memory tile and written out with 16 lanes per row, so every
                     // store instruction covers 2 rows x 256 contiguous bytes (full 128-byte lines) -- for
                     // local HBM and, in multicast mode, for NVLink, where 16-byte-per-row scatter is fatal.
-                    const int cpg = is_f32 ? 2 : 4;                      // 32-column chunks per row group
+                    // chunks per row group: 256-byte row segments when the warp's column span allows it, else 128-byte
                     const int ppc = is_f32 ? 8 : 4;                      // 16-byte pieces per chunk per row
-                    const int cg = (c0 >> 5) & (cpg - 1);                // chunk index inside its group
+                    const int cpg_max = is_f32 ? 2 : 4;
+                    const int cpg = (kColsPerWarp % (cpg_max * 32) == 0) ? cpg_max : cpg_max / 2;
+                    const int ppr = cpg * ppc;                           // 16-byte pieces per staged row: 16 or 8
+                    const int rel = (c0 - col_part * kColsPerWarp) >> 5; // chunk index inside this warp's span
+                    const int cg = rel & (cpg - 1);                      // chunk index inside its group
                     const int ng0 = n0 - cg * 32;                        // first column of the group
-                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4) &&
-                                        ((c0 - cg * 32) + cpg * 32 <= (col_part + 1) * kColsPerWarp);   // warp-uniform; whole group inside the tile
+                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4);   // warp-uniform
                     if (staged) {
-                        const uint32_t st_base = stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u + (uint32_t)lane * 256u;
+                        const uint32_t wbase = stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u;
+                        const uint32_t row_bytes = (uint32_t)ppr * 16u;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (j < ppc) {
-                                const uint32_t phys = (uint32_t)((cg * ppc + j) ^ (lane & 15));
-                                sts_v4(st_base + phys * 16u, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                                const uint32_t phys = (uint32_t)((cg * ppc + j) ^ (lane & (ppr - 1)));
+                                sts_v4(wbase + (uint32_t)lane * row_bytes + phys * 16u, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                             }
                         }
                         if (cg == cpg - 1) {
                             __syncwarp();
                             const int esz = is_f32 ? 4 : 2;
-                            const int piece = lane & 15;
+                            const int piece = lane & (ppr - 1);
+                            const int rows_per_inst = 32 / ppr;          // 2 (256-byte rows) or 4 (128-byte rows)
                             uint8_t* cbase = reinterpret_cast<uint8_t*>(e.C) + (size_t)ng0 * esz + (size_t)piece * 16;
 #pragma unroll 4
-                            for (int i = 0; i < 16; ++i) {
-                                const int rr = 2 * i + (lane >> 4);
+                            for (int i = 0; i < 32 / rows_per_inst; ++i) {
+                                const int rr = rows_per_inst * i + lane / ppr;
                                 const int gm = m_idx + q * 32 + rr;
                                 uint32_t a0, a1, a2, a3;
-                                lds_v4(stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u + (uint32_t)rr * 256u +
-                                       (uint32_t)((piece ^ (rr & 15)) * 16), a0, a1, a2, a3);
+                                lds_v4(wbase + (uint32_t)rr * row_bytes + (uint32_t)((piece ^ (rr & (ppr - 1))) * 16), a0, a1, a2, a3);
                                 if (gm < p.M) stg_v4(cbase + (size_t)gm * e.ldc * esz, a0, a1, a2, a3, p.store_mc);
                             }
                             __syncwarp();
