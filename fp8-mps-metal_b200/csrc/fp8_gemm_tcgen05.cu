@@ -34,7 +34,10 @@ constexpr int kBK = 128;          // bytes of K per stage = one 128B swizzle spa
 constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
 // Epilogue warps: a multiple of 4 (one per TMEM lane quarter); with 8 the two warps of a quarter split the
 // tile's columns.  Measured on C4 (256x256 pair tiles): 4 warps 113.1 us, 8 warps 119.3 us -> 4.
-constexpr int kNumEpiWarps = 4;   // the staging buffer below is sized for 4
+#ifndef FP8B_EPI_WARPS
+#define FP8B_EPI_WARPS 4
+#endif
+constexpr int kNumEpiWarps = FP8B_EPI_WARPS;
 constexpr int kEpiColSplits = kNumEpiWarps / 4;
 constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;
 // Warp roles.  The epilogue takes the LOW warp ids and the two single-thread roles the HIGH ones: the warp
@@ -52,10 +55,11 @@ template <int BN, int CG> struct GemmCfg {
     static constexpr int kBRows = BN / CG;                         // B rows staged by one CTA
     static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (kStageBytes > 32768) ? 4 : (kStageBytes > 24576 ? 6 : 8);
+    static constexpr int kEpiStageBytes = kNumEpiWarps * 8192;    // per epilogue warp: 32 rows x 256 B, XOR-swizzled
+    static constexpr int kStagesFit = (232448 - 1024 - 256 - kEpiStageBytes) / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;   // two accumulators; a power of two >= 32
     static constexpr int kBarBytes = 256;
-    static constexpr int kEpiStageBytes = 4 * 8192;                // per epilogue warp: 32 rows x 256 B, XOR-swizzled
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;   // +1024: manual alignment
 };
 
@@ -197,6 +201,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                  :: "r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// One lane of a fully converged warp; the compiler recognises the elect.sync predicate as "single thread",
+// which lets it keep the tcgen05 / TMA operands in uniform registers without a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // K-major, 128B-swizzled shared-memory operand descriptor (PTX "matrix descriptor", sm_100 version 1):
 //   [0,14)  start address >> 4        [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups      [46,48) version = 1
@@ -290,7 +302,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     if (warp == kWarpTma) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop (uniform control flow); one elected lane issues the TMA traffic.
+        {
+            const bool elected = elect_one();
             int stage = 0; uint32_t phase = 0;
             int issued = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -299,19 +313,22 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
-                    if ((p.debug & 32) && issued >= Cfg::kStages) {
-                        // profiling only: no TMA traffic after the ring is primed (results are garbage)
-                        if (is_leader) mbar_arrive(full_bar(stage));
-                    } else if (CG == 2) {
-                        // both CTAs load their halves; all bytes are accounted on the leader's barrier
-                        if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
-                        tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
-                        tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
-                    } else {
-                        mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                        tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
-                        tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                    if (elected) {
+                        if ((p.debug & 32) && issued >= Cfg::kStages) {
+                            // profiling only: no TMA traffic after the ring is primed (results are garbage)
+                            if (is_leader) mbar_arrive(full_bar(stage));
+                        } else if (CG == 2) {
+                            // both CTAs load their halves; all bytes are accounted on the leader's barrier
+                            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
+                            tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                            tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                        } else {
+                            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                            tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                            tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+                        }
                     }
+                    __syncwarp();
                     ++issued;
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -319,8 +336,15 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else if (warp == kWarpMma) {
         // ===================== MMA issuer =====================
-        if (lane == 0 && is_leader) {
+        // Whole warp in the loop, one elected lane issues.  The loop body is kept minimal: the issuing thread
+        // shares a scheduler with an epilogue warp, and every instruction it needs per k-block is latency the
+        // tensor pipe may have to absorb (measured: a 90-instruction body cost 15 % of MMA throughput).
+        if (is_leader) {
             constexpr uint32_t idesc = make_idesc(kTileM, BN);
+            const bool elected = elect_one();
+            const uint64_t desc_a0 = make_smem_desc(smem_base);
+            const uint64_t desc_b0 = make_smem_desc(smem_base + Cfg::kABytes);
+            constexpr uint64_t kDescStage = (uint64_t)(Cfg::kStageBytes >> 4);      // start-address field per stage
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -332,24 +356,28 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
                     tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                    const uint32_t b_addr = a_addr + Cfg::kABytes;
+                    if (elected) {
+                        const uint64_t adesc = desc_a0 + kDescStage * (uint64_t)stage;
+                        const uint64_t bdesc = desc_b0 + kDescStage * (uint64_t)stage;
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint64_t adesc = make_smem_desc(a_addr + k * kUmmaK);
-                        const uint64_t bdesc = make_smem_desc(b_addr + k * kUmmaK);
-                        if (CG == 2) umma_f8_2sm(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
-                        else umma_f8(d_tmem, adesc, bdesc, idesc, (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {     // +2 in the address field = +32 bytes of K
+                            if (CG == 2) umma_f8_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                            else umma_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        // smem slot free (in both CTAs of a pair) once these MMAs retire
+                        if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     }
-                    // smem slot free (in both CTAs of a pair) once these MMAs retire
-                    if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
+                    __syncwarp();
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
-                if (p.dbg && blockIdx.x == 0) {
-                    const int ti = (tile - worker) / num_workers;
-                    if (ti < 64) { p.dbg[ti * 8 + 0] = t_m0; p.dbg[ti * 8 + 1] = t_m1; p.dbg[ti * 8 + 2] = clock64(); }
+                if (elected) {
+                    if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
+                    if (p.dbg && blockIdx.x == 0) {
+                        const int ti = (tile - worker) / num_workers;
+                        if (ti < 64) { p.dbg[ti * 8 + 0] = t_m0; p.dbg[ti * 8 + 1] = t_m1; p.dbg[ti * 8 + 2] = clock64(); p.dbg[ti * 8 + 3] = 0; }
+                    }
                 }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -640,10 +668,10 @@ static int launch_tcgen05_cfg(const MMArgs& a)
         long long h[64 * 8];
         cudaDeviceSynchronize();
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        printf("tile | mma: wait_tempty  issue+run | epi: wait_tfull  drain+store | epi_end - mma_end\n");
+        printf("tile | mma: wait_tempty  issue+run (of which waiting for TMA) | epi: wait_tfull  drain+store | epi_end - mma_end\n");
         for (int t = 0; t < 64 && h[t * 8 + 2]; ++t)
-            printf("%4d | %8lld %8lld | %8lld %8lld | %8lld   (mma start %lld)\n", t, h[t * 8 + 1] - h[t * 8 + 0],
-                   h[t * 8 + 2] - h[t * 8 + 1], h[t * 8 + 5] - h[t * 8 + 4], h[t * 8 + 6] - h[t * 8 + 5],
+            printf("%4d | %8lld %8lld (%8lld) | %8lld %8lld | %8lld   (mma start %lld)\n", t, h[t * 8 + 1] - h[t * 8 + 0],
+                   h[t * 8 + 2] - h[t * 8 + 1], h[t * 8 + 3], h[t * 8 + 5] - h[t * 8 + 4], h[t * 8 + 6] - h[t * 8 + 5],
                    h[t * 8 + 6] - h[t * 8 + 2], h[t * 8 + 0] - h[0]);
     }
     return after_launch();

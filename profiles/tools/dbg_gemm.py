@@ -6,7 +6,10 @@ from _util import capi
 L=capi(); dev=torch.device('cuda',0)
 M,K,N=4096,3072,12288
 g=torch.Generator(device=dev).manual_seed(0)
-A=torch.randint(0,120,(M,K),dtype=torch.uint8,device=dev,generator=g); B=torch.randint(0,120,(N,K),dtype=torch.uint8,device=dev,generator=g)
+hi=int(os.environ.get('DATA_HI','120'))
+A=torch.randint(0,hi,(M,K),dtype=torch.uint8,device=dev,generator=g); B=torch.randint(0,hi,(N,K),dtype=torch.uint8,device=dev,generator=g)
+if os.environ.get('DATA_NAN_FREE','1')=='1' and hi>127:
+    A=torch.where((A&0x7F)==0x7F, torch.full_like(A,0x3C), A); B=torch.where((B&0x7F)==0x7F, torch.full_like(B,0x3C), B)
 C=torch.empty(M,N,dtype=torch.bfloat16,device=dev); one=torch.full((1,),0.01,device=dev)
 P=lambda t: ctypes.c_void_p(t.data_ptr())
 for i in range(3):

@@ -7,7 +7,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "fp8-mps-metal_b200")
-LIB_PATH = os.path.join(PKG, "libfp8_b200.so")
+LIB_PATH = os.environ.get("FP8B_LIB") or os.path.join(PKG, "libfp8_b200.so")    # FP8B_LIB: A/B a differently built library
 HEADER = os.path.join(ROOT, "include", "fp8_b200.h")
 
 F32, F16, BF16 = 0, 1, 2
