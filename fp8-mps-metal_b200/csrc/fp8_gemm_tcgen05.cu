@@ -67,6 +67,8 @@ struct GemmParams {
     const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    int full_tiles;                          // work items [0, full_tiles) are BN-wide tiles ...
+    int num_work;                            // ... items [full_tiles, num_work) are half-width tiles (last-wave split)
     Epi epi;
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
@@ -248,6 +250,26 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, 
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
+// Work item -> tile.  The last, partially filled wave of BN-wide tiles is cut into half-width tiles so that it
+// takes about half a tile time and ends with a half-size epilogue (C4: 768 tiles on 74 CTA pairs = 10 full
+// rounds + 28 tiles -> 56 half tiles in one short round).
+struct TileCoord { int m_blk; int n0; int width; };
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int bn) {
+    TileCoord c;
+    if (t < p.full_tiles) {
+        c.m_blk = t % p.num_m_blocks;
+        c.n0 = (t / p.num_m_blocks) * bn;
+        c.width = bn;
+    } else {
+        const int u = t - p.full_tiles;
+        const int tt = p.full_tiles + (u >> 1);
+        c.m_blk = tt % p.num_m_blocks;
+        c.width = bn >> 1;
+        c.n0 = (tt / p.num_m_blocks) * bn + (u & 1) * c.width;
+    }
+    return c;
+}
+
 // ------------------------------------------------------------------------------ kernel
 
 template <int BN, int CG>
@@ -298,7 +320,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = p.num_work;
 
     if (warp == kWarpTma) {
         // ===================== TMA producer =====================
@@ -308,8 +330,11 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0; uint32_t phase = 0;
             int issued = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
-                const int m_idx = (tile % p.num_m_blocks) * kTileM + (int)cta_rank * kBM;
-                const int n_idx = (tile / p.num_m_blocks) * BN + (int)cta_rank * Cfg::kBRows;
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+                // each CTA of a pair stages width/CG rows of B (a half-width tile still loads the full box; the
+                // MMA reads only the rows it needs)
+                const int n_idx = tc.n0 + (int)cta_rank * (tc.width / CG);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
@@ -353,6 +378,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tc_fence_after();
                 const long long t_m1 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t idesc_t = (tile < p.full_tiles) ? idesc : make_idesc(kTileM, BN / 2);
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
                     tc_fence_after();
@@ -361,8 +387,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const uint64_t bdesc = desc_b0 + kDescStage * (uint64_t)stage;
 #pragma unroll
                         for (int k = 0; k < kBK / kUmmaK; ++k) {     // +2 in the address field = +32 bytes of K
-                            if (CG == 2) umma_f8_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-                            else umma_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+                            if (CG == 2) umma_f8_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_t, (uint32_t)((kb | k) != 0));
+                            else umma_f8(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc_t, (uint32_t)((kb | k) != 0));
                         }
                         // smem slot free (in both CTAs of a pair) once these MMAs retire
                         if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
@@ -392,8 +418,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const float sb0 = e.sb[0];
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
-            const int m_idx = (tile % p.num_m_blocks) * kTileM + (int)cta_rank * kBM;
-            const int n_idx = (tile / p.num_m_blocks) * BN;
+            const TileCoord tc = decode_tile(p, tile, BN);
+            const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+            const int n_idx = tc.n0;
+            const int cols_per_warp = tc.width / kEpiColSplits;      // kColsPerWarp, or half of it in the split last wave
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
             const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
@@ -403,7 +431,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const long long t_e1 = (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-            for (int c0 = col_part * kColsPerWarp; c0 < (col_part + 1) * kColsPerWarp; c0 += 32) {
+            for (int c0 = col_part * cols_per_warp; c0 < (col_part + 1) * cols_per_warp; c0 += 32) {
                 uint32_t r[32];
                 __syncwarp();                         // lanes may have diverged on the row/column masks below
                 tmem_ld_x32(t_row + c0, r);
@@ -451,7 +479,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
                 tmem_ld_wait();
-                if (c0 + 32 == (col_part + 1) * kColsPerWarp) {   // this warp's last read of the accumulator: hand it back early
+                if (c0 + 32 == (col_part + 1) * cols_per_warp) {   // this warp's last read of the accumulator: hand it back early
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
@@ -506,12 +534,13 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     // chunks per row group: 256-byte row segments when the warp's column span allows it, else 128-byte
                     const int ppc = is_f32 ? 8 : 4;                      // 16-byte pieces per chunk per row
                     const int cpg_max = is_f32 ? 2 : 4;
-                    const int cpg = (kColsPerWarp % (cpg_max * 32) == 0) ? cpg_max : cpg_max / 2;
+                    const int cpg = (cols_per_warp % (cpg_max * 32) == 0) ? cpg_max : cpg_max / 2;
                     const int ppr = cpg * ppc;                           // 16-byte pieces per staged row: 16 or 8
-                    const int rel = (c0 - col_part * kColsPerWarp) >> 5; // chunk index inside this warp's span
+                    const int rel = (c0 - col_part * cols_per_warp) >> 5; // chunk index inside this warp's span
                     const int cg = rel & (cpg - 1);                      // chunk index inside its group
                     const int ng0 = n0 - cg * 32;                        // first column of the group
-                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4);   // warp-uniform
+                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4) &&
+                                        ((rel - cg + cpg) * 32 <= cols_per_warp);   // warp-uniform; the whole group lies in this warp's span
                     if (staged) {
                         const uint32_t wbase = stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u;
                         const uint32_t row_bytes = (uint32_t)ppr * 16u;
@@ -632,6 +661,19 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.num_m_blocks = (a.M + kBM * CG - 1) / (kBM * CG);
     p.num_n_blocks = (a.N + BN - 1) / BN;
     p.num_k_blocks = (a.K + kBK - 1) / kBK;
+    const int tiles_all = p.num_m_blocks * p.num_n_blocks;
+    const int workers_cap = device_info().sm_count / CG;
+    p.full_tiles = tiles_all;
+    p.num_work = tiles_all;
+    {   // split the partially filled last wave into half-width tiles when that makes it one SHORT round
+        const int rem = tiles_all % workers_cap;
+        const bool can_split = (BN % 64 == 0) && ((BN / 2 / CG) % 8 == 0) && tiles_all > workers_cap &&
+                               !(tune_int("FP8B_GEMM_DEBUG", 0) & 8);
+        if (can_split && rem > 0 && 2 * rem <= workers_cap) {
+            p.full_tiles = tiles_all - rem;
+            p.num_work = tiles_all + rem;
+        }
+    }
     p.epi = make_epi(a);
     const size_t esz = dtype_size(a.out_dtype);
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
@@ -648,8 +690,8 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     // multimem.st has no sub-word form: the multicast mode needs every chunk on the 16-byte path
     if (a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
-    const int tiles = p.num_m_blocks * p.num_n_blocks;
-    const int workers_max = device_info().sm_count / CG;            // one CTA (or CTA pair) per SM (pair)
+    const int tiles = p.num_work;
+    const int workers_max = workers_cap;                            // one CTA (or CTA pair) per SM (pair)
     const int workers = tiles < workers_max ? tiles : workers_max;
 
     cudaLaunchConfig_t cfg = {};

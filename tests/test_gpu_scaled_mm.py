@@ -224,6 +224,8 @@ def test_tcgen05_gemm(M, K, N, odt, kw):
     (1000, 1024, 3000, torch.float16, {"bias_dtype": torch.float16}),
     (640, 3072, 1536, torch.bfloat16, {}),                                            # an 8-way shard of the FLUX linear
     (130, 4096, 260, None, {"per_row_b": True}),
+    (2304, 256, 2560, torch.bfloat16, {"per_row_b": True, "bias_dtype": torch.bfloat16}),   # 9x10 pair tiles: 74 + 16 -> last wave split in half-width tiles
+    (2304, 128, 2500, None, {"per_row_a": True}),                                         # same, ragged N, fp32 out
 ])
 def test_tcgen05_all_tile_configs(monkeypatch, cfg, M, K, N, odt, kw):
     """FP8B_GEMM_CFG: 1 = 128x256 tile, one CTA; 2 = 128x128, one CTA; 3 = 256x256, CTA pair
