@@ -58,6 +58,20 @@ inline int launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     return after_launch();
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember it per (kernel instantiation, device).
+// `flags` is a function-local static array of 64 atomics owned by the caller.
+template <typename K>
+inline int ensure_max_smem(K kernel, int bytes, std::atomic<int>* flags)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return FP8B_ERR_NO_DEVICE;
+    if (flags[dev].load(std::memory_order_acquire)) return FP8B_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e);
+    flags[dev].store(1, std::memory_order_release);      // idempotent if two threads race
+    return FP8B_OK;
+}
+
 #ifdef __CUDACC__
 // Programmatic dependent launch, device side.  Both are no-ops when the kernel was not launched with
 // the PDL attribute (or has no predecessor).

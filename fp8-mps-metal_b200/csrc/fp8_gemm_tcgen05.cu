@@ -644,13 +644,8 @@ template <int BN, int CG>
 static int launch_tcgen05_cfg(const MMArgs& a)
 {
     using Cfg = GemmCfg<BN, CG>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(fp8_gemm_tcgen05_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::kSmemBytes);
-    });
-    if (attr_err != cudaSuccess) return cuda_fail(attr_err);
+    static std::atomic<int> attr_done[64];
+    if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG>, Cfg::kSmemBytes, attr_done)) return rc;
 
     CUtensorMap tmap_a, tmap_b;
     if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;

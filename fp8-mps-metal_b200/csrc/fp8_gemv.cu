@@ -221,12 +221,8 @@ bool gemv_supported(const MMArgs& a) { return a.M >= 1 && a.M <= 16; }
 template <int MT, int U>
 static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t st)
 {
-    static bool attr_set = false;                  // benign race: idempotent attribute write
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fp8_gemv_kernel<MT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvMaxSmem);
-        if (e != cudaSuccess) return cuda_fail(e);
-        attr_set = true;
-    }
+    static std::atomic<int> attr_done[64];
+    if (int rc = ensure_max_smem(fp8_gemv_kernel<MT, U>, kGemvMaxSmem, attr_done)) return rc;
     const bool pdl = p.static_b != 0;
     return launch_ex(fp8_gemv_kernel<MT, U>, dim3((p.N + kGemvWarps - 1) / kGemvWarps, S, 1), dim3(kGemvThreads, 1, 1),
                      smem, st, 1, S, pdl, p);

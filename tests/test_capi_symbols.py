@@ -42,3 +42,33 @@ def test_extension_imports_and_refuses_cpu_tensors():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             fp8_mps_native.fp8_encode(torch.zeros(8))          # no CUDA device -> error, not a CPU path
+
+
+def test_compute_entry_points_fail_loudly_without_a_device():
+    """No GPU in this process: every compute entry point returns a negative status (and launches nothing)
+    instead of computing somewhere else.  Argument validation does not need a device either."""
+    import ctypes
+    import torch
+    L = capi()
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("covered by the GPU suite")
+    buf = (ctypes.c_uint8 * 256)()
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    n0 = L.fp8b_launch_count()
+    assert L.fp8b_encode(ptr, 0, ptr, 16, None, None) < 0
+    assert L.fp8b_dequant_f16(ptr, ptr, 16, None, None) < 0
+    assert L.fp8b_dequant(ptr, ptr, 2, 16, None) < 0
+    assert L.fp8b_amax_scale(ptr, 0, 16, ptr, ptr, ptr, None) < 0
+    assert L.fp8b_quantize_rows(ptr, 0, 2, 8, ptr, ptr, None) < 0
+    assert L.fp8b_scaled_mm(ptr, ptr, ptr, 0, 2, 2, 16, 2, ptr, 1, ptr, 1, None, 0, None, None, 0, 0, None) < 0
+    assert L.fp8b_launch_count() == n0
+    # pure validation errors
+    assert L.fp8b_encode(None, 0, ptr, 16, None, None) == -1
+    assert L.fp8b_encode(ptr, 7, ptr, 16, None, None) == -1
+    assert L.fp8b_scaled_mm(ptr, ptr, ptr, 0, 2, 2, 16, 1, ptr, 1, ptr, 1, None, 0, None, None, 0, 0, None) == -1      # ldc < N
+    assert L.fp8b_scaled_mm(ptr, ptr, ptr, 0, 2, 2, 16, 2, ptr, 3, ptr, 1, None, 0, None, None, 0, 0, None) == -1      # bad scale length
+    assert L.fp8b_set_option(99, 1) == -1 and L.fp8b_set_option(1, 0) == 0 and L.fp8b_get_option(0) == 1
+    # empty problems are accepted and do nothing
+    assert L.fp8b_encode(None, 0, None, 0, None, None) == 0
+    assert L.fp8b_scaled_mm(None, None, None, 0, 0, 4, 16, 4, None, 1, None, 1, None, 0, None, None, 0, 0, None) == 0

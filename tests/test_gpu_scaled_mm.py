@@ -339,3 +339,29 @@ def test_native_api_shapes_and_asserts():
     Wq, Ws = fp8_mps_native.fp8_quantize(W)
     r = fp8_mps_native.fp8_scaled_mm(xq, Wq, xs, Ws)
     assert r.shape == (1, 256) and o.rel_rmse(to_np(r), (x @ W.T).numpy()) < 0.15
+
+
+def test_capi_argument_validation():
+    """Error convention of the C ABI (include/fp8_b200.h): negative status, nothing launched, no fallback."""
+    L = capi()
+    A = torch.zeros(4, 64, dtype=torch.uint8, device=DEV)
+    B = torch.zeros(8, 64, dtype=torch.uint8, device=DEV)
+    one = torch.ones(1)
+    n0 = L.fp8b_launch_count()
+    rc, _ = mm_capi(A, B, torch.ones(3), one)                     # scale_a length not in {1, M}
+    assert rc == -1
+    rc, _ = mm_capi(A, B, one, torch.ones(5))                     # scale_b length not in {1, N}
+    assert rc == -1
+    rc, _ = mm_capi(A, B, one, one, algo=9)                       # unknown algorithm
+    assert rc == -1
+    C = torch.empty(4, 8, device=DEV)
+    rc = L.fp8b_scaled_mm(A.data_ptr(), B.data_ptr(), C.data_ptr(), 0, 4, 8, 64, 4, one.to(DEV).data_ptr(), 1,
+                          one.to(DEV).data_ptr(), 1, None, 0, None, None, 0, 0, None)     # ldc < N
+    assert rc == -1
+    rc = L.fp8b_scaled_mm(None, B.data_ptr(), C.data_ptr(), 0, 4, 8, 64, 8, one.to(DEV).data_ptr(), 1,
+                          one.to(DEV).data_ptr(), 1, None, 0, None, None, 0, 0, None)     # null A
+    assert rc == -1
+    assert L.fp8b_launch_count() == n0
+    assert L.fp8b_status_string(-2).startswith(b"unsupported")
+    rc, out = mm_capi(A[:0], B, one, one)                         # M == 0 is a valid empty problem
+    assert rc == 0 and out.shape == (0, 8)
