@@ -424,10 +424,35 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
         rc = L.fp8b_dequant_f16(ctypes.c_void_p(q.data_ptr() + offs[i]), ctypes.c_void_p(h.data_ptr() + 2 * offs[i]), n, None, sp)
         assert rc == 0
 
+    class Span(ctypes.Structure):                      # fp8b_span, include/fp8_b200.h
+        _fields_ = [("inp", ctypes.c_void_p), ("out", ctypes.c_void_p), ("n", ctypes.c_size_t)]
+
+    q_spans = (Span * len(sizes))()
+    d_spans = (Span * len(sizes))()
+    for i, n in enumerate(sizes):
+        q_spans[i].inp, q_spans[i].out, q_spans[i].n = src.data_ptr() + 2 * offs[i], q.data_ptr() + offs[i], n
+        d_spans[i].inp, d_spans[i].out, d_spans[i].n = q.data_ptr() + offs[i], h.data_ptr() + 2 * offs[i], n
+    L.fp8b_encode_batch.restype = ctypes.c_int
+    L.fp8b_encode_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.fp8b_dequant_batch.restype = ctypes.c_int
+    L.fp8b_dequant_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+
+    def quant_batched():
+        rc = L.fp8b_encode_batch(q_spans, len(sizes), 2, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+
+    def dequant_batched():
+        rc = L.fp8b_dequant_batch(d_spans, len(sizes), 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+
     out = {}
     k = max(3, min(steps, 5))
-    for name, one in (("quantize_bf16_to_fp8", quant_one), ("dequant_fp8_to_fp16", dequant_one)):
+    for name, one, batched in (("quantize_bf16_to_fp8", quant_one, quant_batched),
+                               ("dequant_fp8_to_fp16", dequant_one, dequant_batched)):
         res = {}
+        ms_b, launches_b, _, _ = time_graph(torch, batched, k, max(warmup, 3))
+        ms_b /= k
+        gbs_b = 3.0 * total / (ms_b * 1e-3) / 1e9
         for ns in (1, 4):
             ms, launches, _, _ = time_graph(torch, lambda: sweep(one, ns), k, max(warmup, 3))
             ms_sweep = ms / k
@@ -440,7 +465,11 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
                      "launches_per_sweep": launches, "l2": "35.5 GB working set per sweep >> L2",
                      "four_streams": {"ms_per_sweep": round(res[4][0], 3), "value": round(res[4][1], 1), "unit": "GB/s",
                                       "frac": round(res[4][1] / peaks["hbm"], 4),
-                                      "note": "same per-tensor launches issued round-robin on 4 forked streams"}}
+                                      "note": "same per-tensor launches issued round-robin on 4 forked streams"},
+                     "batched_api": {"ms_per_sweep": round(ms_b, 3), "value": round(gbs_b, 1), "unit": "GB/s",
+                                     "frac": round(gbs_b / peaks["hbm"], 4), "launches_per_sweep": launches_b,
+                                     "note": "fp8b_encode_batch / fp8b_dequant_batch: all 304 tensors as one tile list, "
+                                             "one persistent launch (span table in the kernel parameters)"}}
     # spot parity on the last tensor (bit-exact vs the C oracle on a strided sample)
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

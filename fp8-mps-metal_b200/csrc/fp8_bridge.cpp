@@ -158,6 +158,53 @@ torch::Tensor fp8_encode(torch::Tensor input)
     return out;
 }
 
+// Many tensors, one launch per dtype group (fp8b_encode_batch): the checkpoint-conversion path.
+std::vector<torch::Tensor> fp8_encode_many(std::vector<torch::Tensor> inputs)
+{
+    std::vector<torch::Tensor> ins(inputs.size()), outs(inputs.size());
+    if (inputs.empty()) return outs;
+    const auto dev = inputs[0].device();
+    TORCH_CHECK(dev.is_cuda(), "inputs must be CUDA tensors");
+    c10::cuda::CUDAGuard guard(dev);
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        TORCH_CHECK(inputs[i].device() == dev, "all inputs must be on one device");
+        torch::Tensor in = inputs[i].contiguous();
+        if (in.scalar_type() != at::kFloat && in.scalar_type() != at::kHalf && in.scalar_type() != at::kBFloat16)
+            in = in.to(torch::kFloat32);
+        ins[i] = in;
+        outs[i] = torch::empty(in.sizes(), torch::TensorOptions().dtype(torch::kUInt8).device(dev));
+    }
+    for (at::ScalarType dt : {at::kFloat, at::kHalf, at::kBFloat16}) {
+        std::vector<fp8b_span> spans;
+        for (size_t i = 0; i < ins.size(); ++i)
+            if (ins[i].scalar_type() == dt) spans.push_back({ins[i].data_ptr(), outs[i].data_ptr(), (size_t)ins[i].numel()});
+        if (!spans.empty())
+            check_status(fp8b_encode_batch(spans.data(), (int)spans.size(), to_fp8b_dtype(dt), current_stream()),
+                         "fp8b_encode_batch");
+    }
+    return outs;
+}
+
+std::vector<torch::Tensor> fp8_dequantize_many(std::vector<torch::Tensor> inputs, at::ScalarType dtype)
+{
+    std::vector<torch::Tensor> ins(inputs.size()), outs(inputs.size());
+    if (inputs.empty()) return outs;
+    const auto dev = inputs[0].device();
+    TORCH_CHECK(dev.is_cuda(), "inputs must be CUDA tensors");
+    c10::cuda::CUDAGuard guard(dev);
+    std::vector<fp8b_span> spans;
+    for (size_t i = 0; i < inputs.size(); ++i) {
+        TORCH_CHECK(inputs[i].dtype() == torch::kUInt8, "inputs must be uint8");
+        TORCH_CHECK(inputs[i].device() == dev, "all inputs must be on one device");
+        ins[i] = inputs[i].contiguous();
+        outs[i] = torch::empty(ins[i].sizes(), torch::TensorOptions().dtype(dtype).device(dev));
+        spans.push_back({ins[i].data_ptr(), outs[i].data_ptr(), (size_t)ins[i].numel()});
+    }
+    check_status(fp8b_dequant_batch(spans.data(), (int)spans.size(), to_fp8b_dtype(dtype), current_stream()),
+                 "fp8b_dequant_batch");
+    return outs;
+}
+
 std::tuple<torch::Tensor, torch::Tensor> fp8_quantize(torch::Tensor input)
 {
     TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
@@ -232,6 +279,53 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_quantize_rowwise(torch::Tensor inpu
     return std::make_tuple(out, inv);
 }
 
+// Fused per-row fp8_quantize(x) -> scaled matmul for M <= 16 (decode path): x is float, B is uint8 (N,K).
+// Returns (C, inv_scale_a[M]).
+std::tuple<torch::Tensor, torch::Tensor> fp8_linear_dynamic(torch::Tensor x, torch::Tensor B, torch::Tensor scale_b,
+                                                            c10::optional<torch::Tensor> bias,
+                                                            c10::optional<at::ScalarType> out_dtype, bool single_kernel)
+{
+    TORCH_CHECK(B.dtype() == torch::kUInt8, "B must be uint8 (FP8 encoded)");
+    TORCH_CHECK(x.is_cuda() && B.is_cuda() && x.device() == B.device(), "x and B must be CUDA tensors on one device");
+    TORCH_CHECK(x.dim() == 2 && B.dim() == 2 && x.size(1) == B.size(1), "K dimension mismatch between x and B");
+    TORCH_CHECK(B.is_contiguous(), "B must be contiguous");
+    c10::cuda::CUDAGuard guard(x.device());
+    torch::Tensor xin = x.contiguous();
+    if (xin.scalar_type() != at::kFloat && xin.scalar_type() != at::kHalf && xin.scalar_type() != at::kBFloat16)
+        xin = xin.to(torch::kFloat32);
+    const int64_t M = xin.size(0), K = xin.size(1), N = B.size(0);
+    torch::Tensor sb = as_device_f32(scale_b, x.device());
+    TORCH_CHECK(sb.numel() == 1 || sb.numel() == N, "scale_b must have 1 or N elements");
+    torch::Tensor bias_t;
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = bias->to(x.device()).contiguous().reshape({-1});
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    const at::ScalarType odt = out_dtype.value_or(at::kFloat);
+    torch::Tensor C = torch::empty({M, N}, torch::TensorOptions().dtype(odt).device(x.device()));
+    torch::Tensor inv = torch::empty({M}, torch::TensorOptions().dtype(torch::kFloat32).device(x.device()));
+    if (M == 0 || N == 0) return std::make_tuple(C, inv);
+    torch::Tensor ws;
+    void* ws_ptr = nullptr;
+    size_t ws_bytes = 0;
+    if (!single_kernel) {
+        ws_bytes = fp8b_gemv_dynamic_workspace_bytes((int)M, (int)K);
+        ws = torch::empty({(int64_t)ws_bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(x.device()));
+        ws_ptr = ws.data_ptr();
+    }
+    int rc = fp8b_gemv_dynamic(xin.data_ptr(), to_fp8b_dtype(xin.scalar_type()), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt),
+                               (int)M, (int)N, (int)K, N, sb.data_ptr<float>(), (int)sb.numel(), bias_ptr, bias_dt, nullptr,
+                               inv.data_ptr<float>(), ws_ptr, ws_bytes, current_stream());
+    check_status(rc, "fp8b_gemv_dynamic");
+    return std::make_tuple(C, inv);
+}
+
 int64_t select_algo(torch::Tensor A, torch::Tensor B, at::ScalarType out_dtype)
 {
     return fp8b_scaled_mm_select(u8_ptr(A), u8_ptr(B), nullptr, to_fp8b_dtype(out_dtype), (int)A.size(0), (int)B.size(0),
@@ -248,8 +342,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("fp8_dequantize", &fp8_dequantize, "FP8 to float16 dequantization on the GPU",
           py::arg("input"), py::arg("scale"));
     m.def("fp8_quantize", &fp8_quantize, "Float to FP8 quantization on the GPU", py::arg("input"));
+    m.def("fp8_linear_dynamic", &fp8_linear_dynamic, "Fused per-row quantize + FP8 matmul for M <= 16",
+          py::arg("x"), py::arg("B"), py::arg("scale_b"), py::arg("bias") = py::none(), py::arg("out_dtype") = py::none(),
+          py::arg("single_kernel") = false);
     m.def("fp8_quantize_rowwise", &fp8_quantize_rowwise, "Per-row float to FP8 quantization", py::arg("input"));
     m.def("fp8_encode", &fp8_encode, "Float to FP8 encoding without scaling", py::arg("input"));
+    m.def("fp8_encode_many", &fp8_encode_many, "Float to FP8 encoding of a list of tensors in one launch", py::arg("inputs"));
+    m.def("fp8_dequantize_many", &fp8_dequantize_many, "FP8 to float cast of a list of tensors in one launch",
+          py::arg("inputs"), py::arg("dtype"));
     m.def("fp8_dequantize_to", &fp8_dequantize_to, "FP8 to float32/float16/bfloat16 exact cast",
           py::arg("input"), py::arg("dtype"));
     m.def("fp8_scaled_mm_fused", &fp8_scaled_mm_fused,

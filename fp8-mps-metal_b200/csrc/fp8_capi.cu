@@ -157,3 +157,51 @@ extern "C" int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
     return launch_gemm_tcgen05(a);
 }
+
+static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+extern "C" size_t fp8b_gemv_dynamic_workspace_bytes(int M, int K)
+{
+    if (M <= 0 || K <= 0) return 0;
+    return align16((size_t)M * (size_t)K) + align16((size_t)M * sizeof(float));
+}
+
+extern "C" int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
+                                 int M, int N, int K, int64_t ldc,
+                                 const float* scale_b, int scale_b_len,
+                                 const void* bias, int bias_dtype, const float* scale_result,
+                                 float* inv_scale_a_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (M < 0 || N < 0 || K < 0) return FP8B_ERR_INVALID;
+    if (M == 0 || N == 0) return FP8B_OK;
+    if (!X || !B || !C || !scale_b || !valid_dtype(x_dtype) || !valid_dtype(out_dtype)) return FP8B_ERR_INVALID;
+    if (bias && !valid_dtype(bias_dtype)) return FP8B_ERR_INVALID;
+    if (ldc < N || !(scale_b_len == 1 || scale_b_len == N)) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (M > 16 || K < 16 || (K % 16) != 0 || !aligned(B, 16) || !aligned(X, 16)) return FP8B_ERR_UNSUPPORTED;
+    MMArgs a;
+    a.A = nullptr; a.B = B; a.C = C; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_b; a.sa_len = 1;                 // replaced below / unused by the single-kernel path
+    a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = nullptr; a.ws_bytes = 0; a.st = (cudaStream_t)stream; a.store_mc = 0;
+
+    // Two plans.  With a workspace: quantise once (one CTA per row) and chain the GEMV behind it with
+    // programmatic dependent launch -- the GEMV is resident and already streaming its first weight vectors
+    // while the rows are quantised.  Without: one kernel in which every CTA quantises the rows it needs
+    // (cheaper only when the grid is small; it repeats the encode per CTA).
+    const size_t need = fp8b_gemv_dynamic_workspace_bytes(M, K);
+    const int plan = tune_int("FP8B_DYNAMIC_PLAN", 0);         // 1 = force single kernel, 2 = force chain
+    if (workspace && workspace_bytes >= need && aligned(workspace, 16) && plan != 1) {
+        uint8_t* q = static_cast<uint8_t*>(workspace);
+        float* inv = inv_scale_a_out ? inv_scale_a_out
+                                     : reinterpret_cast<float*>(q + align16((size_t)M * (size_t)K));
+        int rc = fp8b_quantize_rows(X, x_dtype, M, (size_t)K, q, inv, stream);
+        if (rc != FP8B_OK) return rc;
+        a.A = q; a.sa = inv; a.sa_len = M;
+        a.chain_pdl = 1;
+        return launch_gemv(a);
+    }
+    if (plan == 2) return FP8B_ERR_INVALID;
+    return launch_gemv_fhfma(a, make_epi(a), X, x_dtype, inv_scale_a_out);
+}

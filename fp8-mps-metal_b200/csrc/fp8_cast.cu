@@ -15,7 +15,6 @@
 namespace fp8b {
 
 constexpr int kCastThreads = 256;
-constexpr int kCastUnroll = 4;
 
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
     uint4 r;
@@ -51,90 +50,92 @@ __device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// FP8 -> wide.  OUT: FP8B_F16 / FP8B_BF16 (8 elements per 16-byte store, 8-byte load) or
-// FP8B_F32 (4 elements per store, 4-byte load).  SCALED (f16 only): fp16 multiply by RN16(scale).
+// Tiles.  A tile is THREADS * UNROLL consecutive 16-byte vectors of the wide side (f16/bf16: 8 elements each,
+// f32: 4) and the matching 8- / 4-byte vectors of the FP8 side; one CTA converts one tile per iteration, every
+// thread keeping UNROLL independent loads in flight (stride THREADS vectors, so a warp touches 512 contiguous
+// bytes per load).  Launch shapes are chosen on the host (cast_shape below): measured on B200, copy-like
+// kernels peak with ~4096 wide vectors (64 KB) in flight per SM and LOSE bandwidth beyond that.
+
+// FP8 -> wide.  OUT: FP8B_F16 / FP8B_BF16 / FP8B_F32.  SCALED (f16 only): fp16 multiply by RN16(scale).
+template <int OUT, bool SCALED, int THREADS, int UNROLL>
+__device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t nvec,
+                                            size_t tile, uint32_t s2)
+{
+    const size_t v0 = tile * (size_t)(THREADS * UNROLL) + threadIdx.x;
+    uint2 w[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t v = v0 + (size_t)u * THREADS;
+        if (OUT == FP8B_F32) w[u] = make_uint2(v < nvec ? ldg_stream_u32(in + v * 4) : 0u, 0u);
+        else w[u] = v < nvec ? ldg_stream_v2(in + v * 8) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t v = v0 + (size_t)u * THREADS;
+        if (v < nvec) {
+            uint4 o;
+            if (OUT == FP8B_F32) {
+                uint32_t lo, hi;
+                dec4_f16x2(w[u].x, lo, hi);
+                const float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
+                const float2 c = __half22float2(*reinterpret_cast<__half2*>(&hi));
+                o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y));
+            } else {
+                dec4_f16x2(w[u].x, o.x, o.y);
+                dec4_f16x2(w[u].y, o.z, o.w);
+                if (SCALED) {                                   // fp16 multiply, native.py:122
+                    const __half2 sc = *reinterpret_cast<const __half2*>(&s2);
+                    uint32_t* q = &o.x;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __half2 r = __hmul2(*reinterpret_cast<__half2*>(&q[j]), sc);
+                        q[j] = *reinterpret_cast<uint32_t*>(&r);
+                    }
+                }
+                if (OUT == FP8B_BF16) {
+                    o.x = f16x2_to_bf16x2(o.x); o.y = f16x2_to_bf16x2(o.y);
+                    o.z = f16x2_to_bf16x2(o.z); o.w = f16x2_to_bf16x2(o.w);
+                }
+            }
+            stg_stream_v4(out + v * 16, o);
+        }
+    }
+}
+
+// ragged tail (< one vector) of a tensor, one thread
 template <int OUT, bool SCALED>
-__global__ void __launch_bounds__(kCastThreads)
+__device__ __forceinline__ void decode_tail(const uint8_t* in, void* out, size_t from, size_t n, const float* scale)
+{
+    for (size_t i = from; i < n; ++i) {
+        const float f = dec1_f32(in[i]);
+        if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
+        else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
+        else {
+            __half h = __float2half_rn(f);
+            if (SCALED) h = __hmul(h, __float2half_rn(__ldg(scale)));
+            reinterpret_cast<__half*>(out)[i] = h;
+        }
+    }
+}
+
+template <int OUT, bool SCALED, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
 fp8_to_wide_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
                    const float* __restrict__ scale)
 {
     constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;            // elements per 16-byte vector
     const size_t nvec = n / EPV;
-    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    const size_t ntiles = (nvec + THREADS * UNROLL - 1) / (THREADS * UNROLL);
     uint32_t s2 = 0;
     if (SCALED) {
         __half2 s = __float2half2_rn(__ldg(scale));           // RN16(scale), native.py:121
         s2 = *reinterpret_cast<uint32_t*>(&s);
     }
-    for (size_t v0 = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v0 < nvec; v0 += stride * kCastUnroll) {
-        if (OUT == FP8B_F32) {
-            uint32_t w[kCastUnroll];
-#pragma unroll
-            for (int u = 0; u < kCastUnroll; ++u) {
-                size_t v = v0 + u * stride;
-                w[u] = v < nvec ? ldg_stream_u32(in + v * 4) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kCastUnroll; ++u) {
-                size_t v = v0 + u * stride;
-                if (v < nvec) {
-                    uint32_t lo, hi;
-                    dec4_f16x2(w[u], lo, hi);
-                    float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
-                    float2 b = __half22float2(*reinterpret_cast<__half2*>(&hi));
-                    uint4 o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y),
-                                         __float_as_uint(b.x), __float_as_uint(b.y));
-                    stg_stream_v4(reinterpret_cast<uint8_t*>(out) + v * 16, o);
-                }
-            }
-        } else {
-            uint2 w[kCastUnroll];
-#pragma unroll
-            for (int u = 0; u < kCastUnroll; ++u) {
-                size_t v = v0 + u * stride;
-                w[u] = v < nvec ? ldg_stream_v2(in + v * 8) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < kCastUnroll; ++u) {
-                size_t v = v0 + u * stride;
-                if (v < nvec) {
-                    uint4 o;
-                    dec4_f16x2(w[u].x, o.x, o.y);
-                    dec4_f16x2(w[u].y, o.z, o.w);
-                    if (SCALED) {                               // fp16 multiply, native.py:122
-                        const __half2 s = *reinterpret_cast<const __half2*>(&s2);
-                        uint32_t* p = &o.x;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __half2 r = __hmul2(*reinterpret_cast<__half2*>(&p[j]), s);
-                            p[j] = *reinterpret_cast<uint32_t*>(&r);
-                        }
-                    }
-                    if (OUT == FP8B_BF16) {
-                        o.x = f16x2_to_bf16x2(o.x); o.y = f16x2_to_bf16x2(o.y);
-                        o.z = f16x2_to_bf16x2(o.z); o.w = f16x2_to_bf16x2(o.w);
-                    }
-                    stg_stream_v4(reinterpret_cast<uint8_t*>(out) + v * 16, o);
-                }
-            }
-        }
-    }
-    // tail (< EPV elements): first thread of the grid, scalar
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (size_t i = nvec * EPV; i < n; ++i) {
-            float f = dec1_f32(in[i]);
-            if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
-            else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
-            else {
-                __half h = __float2half_rn(f);
-                if (SCALED) h = __hmul(h, __float2half_rn(__ldg(scale)));
-                reinterpret_cast<__half*>(out)[i] = h;
-            }
-        }
-    }
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+        decode_tile<OUT, SCALED, THREADS, UNROLL>(in, reinterpret_cast<uint8_t*>(out), nvec, t, s2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) decode_tail<OUT, SCALED>(in, out, nvec * EPV, n, scale);
 }
 
-// Unaligned pointers: same arithmetic, one element per thread-iteration.
 template <int OUT, bool SCALED>
 __global__ void __launch_bounds__(kCastThreads)
 fp8_to_wide_scalar_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
@@ -195,33 +196,40 @@ __device__ __forceinline__ float load_wide_scalar(const void* in, size_t i) {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]);
 }
 
-template <int IN, bool PRESCALE>
-__global__ void __launch_bounds__(kCastThreads)
+template <int IN, bool PRESCALE, int THREADS, int UNROLL>
+__device__ __forceinline__ void encode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t nvec,
+                                            size_t tile, float s)
+{
+    const size_t v0 = tile * (size_t)(THREADS * UNROLL) + threadIdx.x;
+    uint4 w[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t v = v0 + (size_t)u * THREADS;
+        w[u] = v < nvec ? ldg_stream_v4(in + v * 16) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t v = v0 + (size_t)u * THREADS;
+        if (v < nvec) {
+            uint32_t o0, o1;
+            encode_vec<IN, PRESCALE>(w[u], s, o0, o1);
+            if (IN == FP8B_F32) stg_stream_u32(out + v * 4, o0);
+            else stg_stream_v2(out + v * 8, make_uint2(o0, o1));
+        }
+    }
+}
+
+template <int IN, bool PRESCALE, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
 wide_to_fp8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_t n,
                    const float* __restrict__ prescale)
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const size_t nvec = n / EPV;
-    const size_t stride = (size_t)gridDim.x * kCastThreads;
+    const size_t ntiles = (nvec + THREADS * UNROLL - 1) / (THREADS * UNROLL);
     const float s = PRESCALE ? __ldg(prescale) : 1.0f;
-    for (size_t v0 = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v0 < nvec; v0 += stride * kCastUnroll) {
-        uint4 w[kCastUnroll];
-#pragma unroll
-        for (int u = 0; u < kCastUnroll; ++u) {
-            size_t v = v0 + u * stride;
-            w[u] = v < nvec ? ldg_stream_v4(reinterpret_cast<const uint8_t*>(in) + v * 16) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < kCastUnroll; ++u) {
-            size_t v = v0 + u * stride;
-            if (v < nvec) {
-                uint32_t o0, o1;
-                encode_vec<IN, PRESCALE>(w[u], s, o0, o1);
-                if (IN == FP8B_F32) stg_stream_u32(out + v * 4, o0);
-                else stg_stream_v2(out + v * 8, make_uint2(o0, o1));
-            }
-        }
-    }
+    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)
+        encode_tile<IN, PRESCALE, THREADS, UNROLL>(reinterpret_cast<const uint8_t*>(in), out, nvec, t, s);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = nvec * EPV; i < n; ++i) {
             float f = load_wide_scalar<IN>(in, i);
@@ -322,6 +330,7 @@ quantize_rows_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, flo
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     constexpr int ESZ = (IN == FP8B_F32) ? 4 : 2;
+    pdl_launch_dependents();             // fp8b_gemv_dynamic chains a GEMV behind this kernel (it waits before reading out)
     const size_t row = blockIdx.x;
     const uint8_t* rin = reinterpret_cast<const uint8_t*>(in) + row * cols * ESZ;
     uint8_t* rout = out + row * cols;
@@ -370,6 +379,77 @@ quantize_rows_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, flo
         rout[i] = enc1_f32(__fmul_rn(load_wide_scalar<IN>(rin, i), s));
 }
 
+// ------------------------------------------------------------------------------------------
+// Batched casts: MANY tensors in ONE launch (a whole checkpoint's weights; the reference converts them one
+// .to() at a time, fp8_mps_patch.py:143-230).  A per-tensor launch pays ~3 us of ramp + drain on a ~18 us
+// tensor; here the tensors are cut into tiles (see "Tiles" above) and one persistent grid walks
+// the concatenated tile list, so HBM stays saturated across tensor boundaries.  The span table travels in
+// the kernel parameters (constant bank): no device-side descriptor buffer, no host->device copy.
+constexpr int kBatchMaxSpans = 512;
+
+struct CastBatch {
+    int count;
+    uint32_t tile_end[kBatchMaxSpans];      // running total of tiles up to and including span i
+    const void* in[kBatchMaxSpans];
+    void* out[kBatchMaxSpans];
+    size_t n[kBatchMaxSpans];
+};
+
+template <int IN, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+wide_to_fp8_batch_kernel(const __grid_constant__ CastBatch b)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    const uint32_t total = b.tile_end[b.count - 1];
+    int span = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+        while (t >= b.tile_end[span]) ++span;                 // tiles are visited in increasing order
+        const uint32_t t0 = span ? b.tile_end[span - 1] : 0u;
+        const size_t n = b.n[span];
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(b.in[span]);
+        uint8_t* out = reinterpret_cast<uint8_t*>(b.out[span]);
+        encode_tile<IN, false, THREADS, UNROLL>(in, out, n / EPV, t - t0, 1.0f);
+        if (t + 1 == b.tile_end[span] && threadIdx.x == 0)    // ragged tail of this tensor (< EPV elements)
+            for (size_t i = n / EPV * EPV; i < n; ++i) out[i] = enc1_f32(load_wide_scalar<IN>(in, i));
+    }
+}
+
+template <int OUT, int THREADS, int UNROLL>
+__global__ void __launch_bounds__(THREADS)
+fp8_to_wide_batch_kernel(const __grid_constant__ CastBatch b)
+{
+    constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
+    const uint32_t total = b.tile_end[b.count - 1];
+    int span = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+        while (t >= b.tile_end[span]) ++span;
+        const uint32_t t0 = span ? b.tile_end[span - 1] : 0u;
+        const size_t n = b.n[span];
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(b.in[span]);
+        uint8_t* out = reinterpret_cast<uint8_t*>(b.out[span]);
+        decode_tile<OUT, false, THREADS, UNROLL>(in, out, n / EPV, t - t0, 0u);
+        if (t + 1 == b.tile_end[span] && threadIdx.x == 0) decode_tail<OUT, false>(in, out, n / EPV * EPV, n, nullptr);
+    }
+}
+
+// Launch shape for `nvec` wide-side vectors.  Measured on B200 (profiles/tools/cast_exp.py, 12.9 GB per sweep):
+// bandwidth peaks at ~4096 vectors in flight per SM -- wide->fp8 with one 1024-thread CTA x 4 loads per thread
+// (6.36 TB/s; 8 CTAs x 256 x 4 gives 5.7), fp8->wide with one 512-thread CTA x 8 (6.11 TB/s).  Tensors too small
+// to give every SM a big tile use 256-thread x 4 tiles, at most 4 CTAs per SM (same amount in flight).
+struct CastShape { int big; int grid; };
+static CastShape cast_shape(size_t nvec) {
+    const DeviceInfo& di = device_info();
+    CastShape c;
+    const int mode = tune_int("FP8B_CAST_SHAPE", 0);          // profiling knob: 1 = always small tiles, 2 = always big
+    c.big = mode == 2 || (mode == 0 && nvec >= (size_t)di.sm_count * 4096);
+    const size_t tile = c.big ? 4096 : 1024;
+    size_t tiles = (nvec + tile - 1) / tile;
+    if (tiles < 1) tiles = 1;
+    const size_t cap = (size_t)di.sm_count * (c.big ? 1 : 4);
+    c.grid = (int)(tiles < cap ? tiles : cap);
+    return c;
+}
+
 static int cast_grid(size_t work_items) {
     const DeviceInfo& di = device_info();
     size_t want = (work_items + kCastThreads - 1) / kCastThreads;
@@ -382,22 +462,29 @@ static int cast_grid(size_t work_items) {
 
 using namespace fp8b;
 
+// fp8 -> wide launch: big tiles = 512 threads x 8, small = 256 x 4
+template <int OUT, bool SCALED>
+static int launch_decode_vec(const uint8_t* in, void* out, size_t n, const float* scale, cudaStream_t st)
+{
+    constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
+    const CastShape c = cast_shape(n / EPV);
+    if (c.big) fp8_to_wide_kernel<OUT, SCALED, 512, 8><<<c.grid, 512, 0, st>>>(in, out, n, scale);
+    else fp8_to_wide_kernel<OUT, SCALED, 256, 4><<<c.grid, 256, 0, st>>>(in, out, n, scale);
+    return after_launch();
+}
+
 extern "C" int fp8b_dequant_f16(const uint8_t* in, void* out, size_t n, const float* scale, void* stream)
 {
     if (n == 0) return FP8B_OK;
     if (!in || !out) return FP8B_ERR_INVALID;
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = aligned(in, 8) && aligned(out, 16);
-    if (vec) {
-        int g = cast_grid((n / 8 + kCastUnroll - 1) / kCastUnroll);
-        if (scale) fp8_to_wide_kernel<FP8B_F16, true><<<g, kCastThreads, 0, st>>>(in, out, n, scale);
-        else fp8_to_wide_kernel<FP8B_F16, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
-    } else {
-        int g = cast_grid(n);
-        if (scale) fp8_to_wide_scalar_kernel<FP8B_F16, true><<<g, kCastThreads, 0, st>>>(in, out, n, scale);
-        else fp8_to_wide_scalar_kernel<FP8B_F16, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
-    }
+    if (aligned(in, 8) && aligned(out, 16))
+        return scale ? launch_decode_vec<FP8B_F16, true>(in, out, n, scale, st)
+                     : launch_decode_vec<FP8B_F16, false>(in, out, n, nullptr, st);
+    const int g = cast_grid(n);
+    if (scale) fp8_to_wide_scalar_kernel<FP8B_F16, true><<<g, kCastThreads, 0, st>>>(in, out, n, scale);
+    else fp8_to_wide_scalar_kernel<FP8B_F16, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
     return after_launch();
 }
 
@@ -410,16 +497,23 @@ extern "C" int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t 
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == FP8B_BF16) {
-        if (aligned(in, 8) && aligned(out, 16))
-            fp8_to_wide_kernel<FP8B_BF16, false><<<cast_grid((n / 8 + kCastUnroll - 1) / kCastUnroll), kCastThreads, 0, st>>>(in, out, n, nullptr);
-        else
-            fp8_to_wide_scalar_kernel<FP8B_BF16, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
+        if (aligned(in, 8) && aligned(out, 16)) return launch_decode_vec<FP8B_BF16, false>(in, out, n, nullptr, st);
+        fp8_to_wide_scalar_kernel<FP8B_BF16, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
     } else {
-        if (aligned(in, 4) && aligned(out, 16))
-            fp8_to_wide_kernel<FP8B_F32, false><<<cast_grid((n / 4 + kCastUnroll - 1) / kCastUnroll), kCastThreads, 0, st>>>(in, out, n, nullptr);
-        else
-            fp8_to_wide_scalar_kernel<FP8B_F32, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
+        if (aligned(in, 4) && aligned(out, 16)) return launch_decode_vec<FP8B_F32, false>(in, out, n, nullptr, st);
+        fp8_to_wide_scalar_kernel<FP8B_F32, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
     }
+    return after_launch();
+}
+
+// wide -> fp8 launch: big tiles = 1024 threads x 4, small = 256 x 4
+template <int IN, bool PRESCALE>
+static int launch_encode_vec(const void* in, uint8_t* out, size_t n, const float* prescale, cudaStream_t st)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    const CastShape c = cast_shape(n / EPV);
+    if (c.big) wide_to_fp8_kernel<IN, PRESCALE, 1024, 4><<<c.grid, 1024, 0, st>>>(in, out, n, prescale);
+    else wide_to_fp8_kernel<IN, PRESCALE, 256, 4><<<c.grid, 256, 0, st>>>(in, out, n, prescale);
     return after_launch();
 }
 
@@ -427,16 +521,12 @@ template <int IN>
 static int launch_encode(const void* in, uint8_t* out, size_t n, const float* prescale, cudaStream_t st)
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
-    const bool vec = aligned(in, 16) && aligned(out, EPV);
-    if (vec) {
-        int g = cast_grid((n / EPV + kCastUnroll - 1) / kCastUnroll);
-        if (prescale) wide_to_fp8_kernel<IN, true><<<g, kCastThreads, 0, st>>>(in, out, n, prescale);
-        else wide_to_fp8_kernel<IN, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
-    } else {
-        int g = cast_grid(n);
-        if (prescale) wide_to_fp8_scalar_kernel<IN, true><<<g, kCastThreads, 0, st>>>(in, out, n, prescale);
-        else wide_to_fp8_scalar_kernel<IN, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
-    }
+    if (aligned(in, 16) && aligned(out, EPV))
+        return prescale ? launch_encode_vec<IN, true>(in, out, n, prescale, st)
+                        : launch_encode_vec<IN, false>(in, out, n, nullptr, st);
+    const int g = cast_grid(n);
+    if (prescale) wide_to_fp8_scalar_kernel<IN, true><<<g, kCastThreads, 0, st>>>(in, out, n, prescale);
+    else wide_to_fp8_scalar_kernel<IN, false><<<g, kCastThreads, 0, st>>>(in, out, n, nullptr);
     return after_launch();
 }
 
@@ -459,6 +549,105 @@ static int launch_amax(const void* in, size_t n, uint32_t* scratch, cudaStream_t
     if (aligned(in, 16)) amax_kernel<IN><<<cast_grid(n / EPV + 1), kCastThreads, 0, st>>>(in, n, scratch);
     else amax_scalar_kernel<IN><<<cast_grid(n), kCastThreads, 0, st>>>(in, n, scratch);
     return after_launch();
+}
+
+// ---- batched entry points ------------------------------------------------------------------
+namespace {
+
+// Collects aligned, non-empty spans into CastBatch tables and launches one persistent grid per table.
+// epv: elements per wide-side vector; fp8_in: true for fp8 -> wide.  launch(table, grid, big).
+template <typename LaunchFn, typename SingleFn>
+int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, LaunchFn launch, SingleFn single)
+{
+    if (count < 0 || (count > 0 && !spans)) return FP8B_ERR_INVALID;
+    for (int i = 0; i < count; ++i)
+        if (spans[i].n != 0 && (!spans[i].in || !spans[i].out)) return FP8B_ERR_INVALID;
+    if (count == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    auto vec_ok = [&](const fp8b_span& sp) {
+        return aligned(fp8_in ? sp.out : sp.in, 16) && aligned(fp8_in ? sp.in : sp.out, epv);
+    };
+    // tile size for the whole call, from the total amount of vector work (cast_shape)
+    uint64_t total_vecs = 0;
+    for (int i = 0; i < count; ++i) if (spans[i].n && vec_ok(spans[i])) total_vecs += spans[i].n / epv;
+    const CastShape shape = cast_shape((size_t)total_vecs);
+    const uint64_t tile_vecs = shape.big ? 4096 : 1024;
+    const uint64_t cap = (uint64_t)device_info().sm_count * (shape.big ? 1 : 4);
+    CastBatch b;
+    b.count = 0;
+    uint64_t tiles = 0;
+    auto flush = [&]() -> int {
+        if (b.count == 0) return FP8B_OK;
+        const int rc = launch(b, (int)(tiles < cap ? tiles : cap), shape.big);
+        b.count = 0; tiles = 0;
+        return rc;
+    };
+    for (int i = 0; i < count; ++i) {
+        const fp8b_span& sp = spans[i];
+        if (sp.n == 0) continue;
+        if (!vec_ok(sp)) {                                             // rare: scalar single-tensor path
+            if (int rc = single(sp)) return rc;
+            continue;
+        }
+        const uint64_t nvec = sp.n / epv;
+        uint64_t t = (nvec + tile_vecs - 1) / tile_vecs;
+        if (t == 0) t = 1;                                             // n < epv: one tile for the scalar tail
+        if (t > 0xFFFFFFFFull) { if (int rc = single(sp)) return rc; continue; }
+        if (b.count == kBatchMaxSpans || tiles + t > 0xFFFFFFFFull) { if (int rc = flush()) return rc; }
+        tiles += t;
+        b.tile_end[b.count] = (uint32_t)tiles;
+        b.in[b.count] = sp.in; b.out[b.count] = sp.out; b.n[b.count] = sp.n;
+        ++b.count;
+    }
+    return flush();
+}
+
+template <int IN>
+int launch_encode_batch(const CastBatch& b, int grid, int big, cudaStream_t st)
+{
+    if (big) wide_to_fp8_batch_kernel<IN, 1024, 4><<<grid, 1024, 0, st>>>(b);
+    else wide_to_fp8_batch_kernel<IN, 256, 4><<<grid, 256, 0, st>>>(b);
+    return after_launch();
+}
+
+template <int OUT>
+int launch_decode_batch(const CastBatch& b, int grid, int big, cudaStream_t st)
+{
+    if (big) fp8_to_wide_batch_kernel<OUT, 512, 8><<<grid, 512, 0, st>>>(b);
+    else fp8_to_wide_batch_kernel<OUT, 256, 4><<<grid, 256, 0, st>>>(b);
+    return after_launch();
+}
+
+}  // namespace
+
+extern "C" int fp8b_encode_batch(const fp8b_span* spans, int count, int in_dtype, void* stream)
+{
+    if (!valid_dtype(in_dtype)) return FP8B_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto launch = [&](const CastBatch& b, int grid, int big) -> int {
+        if (in_dtype == FP8B_F32) return launch_encode_batch<FP8B_F32>(b, grid, big, st);
+        if (in_dtype == FP8B_F16) return launch_encode_batch<FP8B_F16>(b, grid, big, st);
+        return launch_encode_batch<FP8B_BF16>(b, grid, big, st);
+    };
+    auto single = [&](const fp8b_span& sp) -> int {
+        return fp8b_encode(sp.in, in_dtype, static_cast<uint8_t*>(sp.out), sp.n, nullptr, stream);
+    };
+    return run_batch(spans, count, in_dtype == FP8B_F32 ? 4 : 8, false, launch, single);
+}
+
+extern "C" int fp8b_dequant_batch(const fp8b_span* spans, int count, int out_dtype, void* stream)
+{
+    if (!valid_dtype(out_dtype)) return FP8B_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto launch = [&](const CastBatch& b, int grid, int big) -> int {
+        if (out_dtype == FP8B_F32) return launch_decode_batch<FP8B_F32>(b, grid, big, st);
+        if (out_dtype == FP8B_F16) return launch_decode_batch<FP8B_F16>(b, grid, big, st);
+        return launch_decode_batch<FP8B_BF16>(b, grid, big, st);
+    };
+    auto single = [&](const fp8b_span& sp) -> int {
+        return fp8b_dequant(static_cast<const uint8_t*>(sp.in), sp.out, out_dtype, sp.n, stream);
+    };
+    return run_batch(spans, count, out_dtype == FP8B_F32 ? 4 : 8, true, launch, single);
 }
 
 extern "C" int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* scale_out, float* inv_scale_out,

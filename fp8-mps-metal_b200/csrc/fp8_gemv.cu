@@ -46,9 +46,26 @@ struct GemvParams {
     Epi epi;
 };
 
+// fused dynamic-quantisation kernel: GemvParams (A unused) + the un-quantised activations
+struct GemvXqParams {
+    GemvParams g;
+    const void* X;         // (M,K) of x_dtype, row m0 first
+    int x_dtype;
+    float* inv_scale_out;  // optional [M] output of the per-row inverse scales (may be null)
+};
+
 __device__ __forceinline__ uint4 ldg_w_v4(const uint8_t* p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// Activations: coherent load.  x is typically written by the predecessor kernel; ptxas hoists non-coherent
+// (.nc / __ldg) loads above griddepcontrol.wait, so those must never be used for it.
+__device__ __forceinline__ uint4 ld_x_v4(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
@@ -59,6 +76,48 @@ __device__ __forceinline__ void fhfma2(float& acc, uint32_t w2, uint32_t x2) {
         "mov.b32 {a0, a1}, %1;\n\tmov.b32 {b0, b1}, %2;\n\t"
         "fma.rn.f32.f16 %0, a0, b0, %0;\n\tfma.rn.f32.f16 %0, a1, b1, %0;\n\t}"
         : "+f"(acc) : "r"(w2), "r"(x2));
+}
+
+__device__ __forceinline__ float gemv_load_x(const void* x, int dtype, size_t i) {
+    if (dtype == FP8B_F32) return reinterpret_cast<const float*>(x)[i];
+    if (dtype == FP8B_F16) return __half2float(reinterpret_cast<const __half*>(x)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+}
+
+// 16 consecutive activations as fp32 (16-byte loads; i is a multiple of 16 and X is 16-byte aligned)
+__device__ __forceinline__ void xq_load16(const void* x, int dtype, size_t i, float (&f)[16]) {
+    if (dtype == FP8B_F32) {
+        const float4* v = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + i);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 q = v[j]; f[4 * j] = q.x; f[4 * j + 1] = q.y; f[4 * j + 2] = q.z; f[4 * j + 3] = q.w; }
+    } else {
+        const uint4* v = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(x) + i);
+        uint32_t w[8];
+        { const uint4 q0 = v[0], q1 = v[1]; w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w; w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w; }
+        if (dtype == FP8B_F16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                f[2 * j] = t.x; f[2 * j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[2 * j] = __uint_as_float(w[j] << 16); f[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+        }
+    }
+}
+
+// quantised value of one activation, as the reference composition fp8_quantize -> kernel decode sees it
+__device__ __forceinline__ float gemv_xq_value(const void* x, int dtype, size_t i, float scale) {
+    return dec1_f32(enc1_f32(__fmul_rn(gemv_load_x(x, dtype, i), scale)));
+}
+
+// masked reference dot product for the XQ kernels (NaN weight bytes contribute 0, fp8_matmul.metal:21)
+static __device__ __noinline__ float slow_dot_masked_xq(const void* x, int dtype, size_t x_off, float scale,
+                                                        const uint8_t* __restrict__ b, int K) {
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s = __fmaf_rn(gemv_xq_value(x, dtype, x_off + k, scale), dec1_f32(b[k]), s);
+    return s;
 }
 
 template <int MT>
@@ -126,7 +185,7 @@ fp8_gemv_kernel(const GemvParams p)
         // stage x[:, kp : kp+len] as fp16 (raw hardware decode; NaN bytes stay NaN on purpose)
         for (int i = threadIdx.x; i < MT * nvec; i += kGemvThreads) {
             const int m = i / nvec, v = i - m * nvec;
-            const uint4 xb = __ldg(reinterpret_cast<const uint4*>(p.A + (size_t)m * K + kp) + v);
+            const uint4 xb = ld_x_v4(p.A + (size_t)m * K + kp + (size_t)v * 16);
             uint4 lo, hi;
             dec4_f16x2_raw(xb.x, lo.x, lo.y);
             dec4_f16x2_raw(xb.y, lo.z, lo.w);
@@ -198,6 +257,195 @@ fp8_gemv_kernel(const GemvParams p)
     cluster.sync();
 }
 
+// Fused dynamic quantisation: the activations arrive UN-quantised (f32/f16/bf16).  Every CTA computes each row's amax, the
+// reference's double-precision scale 448/amax (fp8_mps_native.py:174-176) and stages enc(x*scale) decoded to
+// fp16 -- the composition fp8_quantize(x) -> _scaled_mm in ONE launch, bit-identical in the quantised values,
+// with the inverse scale applied in the epilogue as scale_a.
+template <int MT, int U>
+__global__ void __launch_bounds__(kGemvThreads)
+fp8_gemv_xq_kernel(const GemvXqParams xp)
+{
+    const GemvParams& p = xp.g;
+    constexpr bool XQ = true;      // (the body keeps the structure of fp8_gemv_kernel; a shared template cost that kernel 2 %)
+    extern __shared__ __align__(16) uint8_t gemv_smem[];
+    uint4* xs = reinterpret_cast<uint4*>(gemv_smem);
+    __shared__ float part[kGemvWarps][kGemvMaxMT];
+    __shared__ float xq_scale[kGemvMaxMT], xq_inv[kGemvMaxMT];
+    __shared__ uint32_t xq_red[kGemvWarps];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kGemvWarps + warp;
+    const bool row_ok = row < p.N;
+    const int K = p.K;
+    const int k_begin = blockIdx.y * p.k_per_split;
+    const int k_end = min(K, k_begin + p.k_per_split);
+    const uint8_t* wrow = p.B + (size_t)(row_ok ? row : 0) * K;
+
+    float acc0[MT], acc1[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { acc0[m] = 0.0f; acc1[m] = 0.0f; }
+
+    // Programmatic dependent launch (see fp8_b200.h, FP8B_OPT_STATIC_WEIGHTS): the next kernel may start
+    // scheduling now; we wait for our predecessor before reading anything it may have written -- all
+    // inputs by default, everything except the weights when they are declared static.
+    pdl_launch_dependents();
+    bool need_wait = p.static_b != 0;
+    if (!need_wait) pdl_wait();
+
+    if (XQ) {
+        // per-row amax over the FULL K range (every CTA recomputes it: x is tiny next to its weight rows and
+        // L2-resident after the first CTA).  16-byte loads; |x| compared on the bit patterns.
+        if (need_wait) { pdl_wait(); need_wait = false; }
+        for (int m = 0; m < MT; ++m) {
+            uint32_t mx = 0;
+            if (xp.x_dtype == FP8B_F32) {
+                const uint4* xv = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(xp.X) + (size_t)m * K);
+                for (int i = threadIdx.x; i < (K >> 2); i += kGemvThreads) {
+                    const uint4 q = xv[i];
+                    mx = max(max(mx, q.x & 0x7FFFFFFFu), max(q.y & 0x7FFFFFFFu, max(q.z & 0x7FFFFFFFu, q.w & 0x7FFFFFFFu)));
+                }
+            } else {
+                const uint4* xv = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(xp.X) + (size_t)m * K);
+                uint32_t m2 = 0;                                    // two u16 maxima side by side
+                for (int i = threadIdx.x; i < (K >> 3); i += kGemvThreads) {
+                    const uint4 q = xv[i];
+                    m2 = __vmaxu2(__vmaxu2(m2, q.x & 0x7FFF7FFFu),
+                                  __vmaxu2(__vmaxu2(q.y & 0x7FFF7FFFu, q.z & 0x7FFF7FFFu), q.w & 0x7FFF7FFFu));
+                }
+                const uint32_t h = max(m2 & 0xFFFFu, m2 >> 16);
+                mx = xp.x_dtype == FP8B_F16 ? __float_as_uint(__half2float(__ushort_as_half((unsigned short)h))) : (h << 16);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+            if (lane == 0) xq_red[warp] = mx;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t mm = 0;
+                for (int w = 0; w < kGemvWarps; ++w) mm = max(mm, xq_red[w]);
+                const float amax = __uint_as_float(mm);
+                const double sc = (amax > 0.0f) ? 448.0 / (double)amax : 1.0;      // fp8_mps_native.py:175-176
+                xq_scale[m] = (float)sc;
+                xq_inv[m] = (float)(1.0 / sc);                                      // :189
+                if (xp.inv_scale_out && blockIdx.x == 0 && blockIdx.y == 0) xp.inv_scale_out[m] = (float)(1.0 / sc);
+            }
+            __syncthreads();
+        }
+    }
+
+    for (int kp = k_begin; kp < k_end; kp += p.k_panel) {
+        const int len = min(k_end - kp, p.k_panel);
+        const int nvec = len >> 4;
+        const int nvec_panel = p.k_panel >> 4;
+        const uint8_t* wp = wrow + kp;
+        // first batch of weight vectors goes in flight BEFORE x is staged, so the prologue
+        // (x load + decode + barrier) overlaps the first HBM round trip
+        uint4 cur[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int vv = lane + 32 * u;
+            cur[u] = (row_ok && vv < nvec) ? ldg_w_v4(wp + (size_t)vv * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (need_wait) { pdl_wait(); need_wait = false; }
+        if (kp != k_begin) __syncthreads();
+        // stage x[:, kp : kp+len] as fp16 (raw hardware decode; NaN bytes stay NaN on purpose)
+        for (int i = threadIdx.x; i < MT * nvec; i += kGemvThreads) {
+            const int m = i / nvec, v = i - m * nvec;
+            uint4 xb;
+            if (XQ) {
+                const size_t base = (size_t)m * K + kp + (size_t)v * 16;
+                const float sc = xq_scale[m];
+                float f[16];
+                xq_load16(xp.X, xp.x_dtype, base, f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __fmul_rn(f[j], sc);                                    // native.py:179
+                xb.x = enc4_f32(f[0], f[1], f[2], f[3]);
+                xb.y = enc4_f32(f[4], f[5], f[6], f[7]);
+                xb.z = enc4_f32(f[8], f[9], f[10], f[11]);
+                xb.w = enc4_f32(f[12], f[13], f[14], f[15]);
+            } else {
+                xb = ld_x_v4(p.A + (size_t)m * K + kp + (size_t)v * 16);
+            }
+            uint4 lo, hi;
+            dec4_f16x2_raw(xb.x, lo.x, lo.y);
+            dec4_f16x2_raw(xb.y, lo.z, lo.w);
+            dec4_f16x2_raw(xb.z, hi.x, hi.y);
+            dec4_f16x2_raw(xb.w, hi.z, hi.w);
+            xs[(m * 2 + 0) * nvec_panel + v] = lo;
+            xs[(m * 2 + 1) * nvec_panel + v] = hi;
+        }
+        __syncthreads();
+        if (row_ok) {
+            for (int v = lane; v < nvec; v += 32 * U) {
+                uint4 nxt[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {                       // next batch in flight while this one is consumed
+                    const int vv = v + 32 * (U + u);
+                    nxt[u] = vv < nvec ? ldg_w_v4(wp + (size_t)vv * 16) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int vv = v + 32 * u;
+                    if (vv < nvec) gemv_consume<MT>(cur[u], xs, nvec_panel, vv, acc0, acc1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            }
+        }
+    }
+
+    if (need_wait) pdl_wait();                       // empty K range: still order the stores below
+    float s[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        float t = acc0[m] + acc1[m];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, o);
+        s[m] = t;
+    }
+
+    const int S = gridDim.y;
+    if (S == 1) {
+        if (row_ok && lane < MT) {
+            float v = 0.0f;
+#pragma unroll
+            for (int m = 0; m < MT; ++m) if (lane == m) v = s[m];
+            const int gm = p.m0 + lane;
+            if (XQ) {
+                if (v != v) v = slow_dot_masked_xq(xp.X, xp.x_dtype, (size_t)lane * K, xq_scale[lane], wrow, K);
+                epi_store(p.epi, gm, row, epi_apply_sa(p.epi, v, xq_inv[lane], row));
+            } else {
+                if (v != v) v = slow_dot_masked(p.A + (size_t)lane * K, wrow, K);
+                epi_store(p.epi, gm, row, epi_apply(p.epi, v, gm, row));
+            }
+        }
+        return;
+    }
+
+    // split-K: reduce the S partial sums through distributed shared memory, in rank order
+    cg::cluster_group cluster = cg::this_cluster();
+    if (lane == 0) {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) part[warp][m] = s[m];
+    }
+    cluster.sync();
+    if (cluster.block_rank() == 0 && row_ok && lane < MT) {
+        float v = 0.0f;
+        for (int r = 0; r < S; ++r) {
+            const float* rp = cluster.map_shared_rank(&part[0][0], r);
+            v += rp[warp * kGemvMaxMT + lane];
+        }
+        const int gm = p.m0 + lane;
+        if (XQ) {
+            if (v != v) v = slow_dot_masked_xq(xp.X, xp.x_dtype, (size_t)lane * K, xq_scale[lane], wrow, K);
+            epi_store(p.epi, gm, row, epi_apply_sa(p.epi, v, xq_inv[lane], row));
+        } else {
+            if (v != v) v = slow_dot_masked(p.A + (size_t)lane * K, wrow, K);
+            epi_store(p.epi, gm, row, epi_apply(p.epi, v, gm, row));
+        }
+    }
+    cluster.sync();
+}
+
 // Any K / any alignment: byte loads, masked scalar decode, fp32 FMA.  Correct, not fast.
 __global__ void __launch_bounds__(kGemvThreads)
 fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi)
@@ -228,6 +476,18 @@ static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t 
                      smem, st, 1, S, pdl, p);
 }
 
+template <int MT, int U>
+static int launch_gemv_xq_mt(const GemvXqParams& xp, int S, size_t smem, cudaStream_t st)
+{
+    static std::atomic<int> attr_done[64];
+    if (int rc = ensure_max_smem(fp8_gemv_xq_kernel<MT, U>, kGemvMaxSmem, attr_done)) return rc;
+    const bool pdl = xp.g.static_b != 0;
+    return launch_ex(fp8_gemv_xq_kernel<MT, U>, dim3((xp.g.N + kGemvWarps - 1) / kGemvWarps, S, 1), dim3(kGemvThreads, 1, 1),
+                     smem, st, 1, S, pdl, xp);
+}
+
+int launch_gemv_fhfma(const MMArgs& a, const Epi& epi, const void* X, int x_dtype, float* inv_scale_out);
+
 int launch_gemv(const MMArgs& a)
 {
     if (!gemv_supported(a)) return FP8B_ERR_UNSUPPORTED;
@@ -243,8 +503,15 @@ int launch_gemv(const MMArgs& a)
         fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi);
         return after_launch();
     }
+    return launch_gemv_fhfma(a, epi, nullptr, 0, nullptr);
+}
+
+// Shared launch planning for the FHFMA kernel: A = fp8 bytes (X == nullptr) or X = un-quantised activations.
+int launch_gemv_fhfma(const MMArgs& a, const Epi& epi, const void* X, int x_dtype, float* inv_scale_out)
+{
     const DeviceInfo& di = device_info();
     const int row_blocks = (a.N + kGemvWarps - 1) / kGemvWarps;
+    const size_t x_esz = X ? dtype_size(x_dtype) : 1;
     for (int m0 = 0; m0 < a.M; m0 += kGemvMaxMT) {
         const int mt = a.M - m0 < kGemvMaxMT ? a.M - m0 : kGemvMaxMT;
         // split K over a cluster until the grid covers the GPU about twice (each CTA keeps >= 2 KB of K)
@@ -257,18 +524,32 @@ int launch_gemv(const MMArgs& a)
         const int max_panel = (kGemvMaxSmem / (2 * mt)) & ~15;
         if (panel > max_panel) panel = max_panel;
         GemvParams p;
-        p.A = a.A + (size_t)m0 * a.K; p.B = a.B; p.m0 = m0; p.N = a.N; p.K = a.K;
+        p.A = X ? nullptr : a.A + (size_t)m0 * a.K; p.B = a.B; p.m0 = m0; p.N = a.N; p.K = a.K;
         p.k_per_split = kps; p.k_panel = panel; p.epi = epi;
-        p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && g_opt_static_weights.load(std::memory_order_relaxed)) ? 1 : 0;
+        p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && (a.chain_pdl || g_opt_static_weights.load(std::memory_order_relaxed))) ? 1 : 0;
         const size_t smem = (size_t)mt * panel * 2;
         int rc;
-        const int unroll = tune_int("FP8B_GEMV_UNROLL", 4);
-        switch (mt) {
-            case 1: rc = unroll == 2 ? launch_gemv_mt<1, 2>(p, S, smem, a.st)
-                       : unroll == 8 ? launch_gemv_mt<1, 8>(p, S, smem, a.st) : launch_gemv_mt<1, 4>(p, S, smem, a.st); break;
-            case 2: rc = launch_gemv_mt<2, 4>(p, S, smem, a.st); break;
-            case 3: rc = launch_gemv_mt<3, 4>(p, S, smem, a.st); break;
-            default: rc = launch_gemv_mt<4, 4>(p, S, smem, a.st); break;
+        if (X) {
+            GemvXqParams xp;
+            xp.g = p;
+            xp.X = static_cast<const uint8_t*>(X) + (size_t)m0 * a.K * x_esz;
+            xp.x_dtype = x_dtype;
+            xp.inv_scale_out = inv_scale_out ? inv_scale_out + m0 : nullptr;
+            switch (mt) {
+                case 1: rc = launch_gemv_xq_mt<1, 4>(xp, S, smem, a.st); break;
+                case 2: rc = launch_gemv_xq_mt<2, 4>(xp, S, smem, a.st); break;
+                case 3: rc = launch_gemv_xq_mt<3, 4>(xp, S, smem, a.st); break;
+                default: rc = launch_gemv_xq_mt<4, 4>(xp, S, smem, a.st); break;
+            }
+        } else {
+            const int unroll = tune_int("FP8B_GEMV_UNROLL", 4);
+            switch (mt) {
+                case 1: rc = unroll == 2 ? launch_gemv_mt<1, 2>(p, S, smem, a.st)
+                           : unroll == 8 ? launch_gemv_mt<1, 8>(p, S, smem, a.st) : launch_gemv_mt<1, 4>(p, S, smem, a.st); break;
+                case 2: rc = launch_gemv_mt<2, 4>(p, S, smem, a.st); break;
+                case 3: rc = launch_gemv_mt<3, 4>(p, S, smem, a.st); break;
+                default: rc = launch_gemv_mt<4, 4>(p, S, smem, a.st); break;
+            }
         }
         if (rc != FP8B_OK) return rc;
     }

@@ -42,7 +42,9 @@ __device__ __forceinline__ uint4 ldg_stream16(const uint8_t* p) {
 }
 __device__ __forceinline__ uint4 ldg_cached16(const uint8_t* p) {
     uint4 r;
-    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+    // NOT .nc: x is typically written by the predecessor kernel, and ptxas moves non-coherent loads above
+    // griddepcontrol.wait (seen in SASS: LDG.CONSTANT ahead of ACQBULK), which reads stale activations.
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
@@ -165,7 +167,7 @@ int launch_gemv_mma(const MMArgs& a)
     p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
     p.k_per_warp = (((a.K + kMmaWarps - 1) / kMmaWarps) + 63) & ~63;
     p.epi = make_epi(a);
-    p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && g_opt_static_weights.load(std::memory_order_relaxed)) ? 1 : 0;
+    p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && (a.chain_pdl || g_opt_static_weights.load(std::memory_order_relaxed))) ? 1 : 0;
     const bool pdl = p.static_b != 0;      // without static weights PDL only hides launch latency, which graphs already do
     const int grid = (a.N + kMmaRows - 1) / kMmaRows;
     const int batch = tune_int("FP8B_GEMV_BATCH", 4);

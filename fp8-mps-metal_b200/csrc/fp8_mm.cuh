@@ -22,6 +22,8 @@ struct MMArgs {
     void* ws; size_t ws_bytes;
     int store_mc;          // tcgen05 kernel only: C is a multicast address (multimem.st)
     cudaStream_t st;
+    int chain_pdl = 0;     // GEMV only: the predecessor on the stream is our own quantise kernel (never writes B),
+                           // so launch with PDL and prefetch B before griddepcontrol.wait
 };
 
 bool gemv_supported(const MMArgs& a);
@@ -54,6 +56,9 @@ inline Epi make_epi(const MMArgs& a) {
     return e;
 }
 
+// FHFMA GEMV planner shared by the pre-quantised path (X == nullptr) and the fused dynamic-quantise path.
+int launch_gemv_fhfma(const MMArgs& a, const Epi& epi, const void* X, int x_dtype, float* inv_scale_out);
+
 // NOTE: plain loads, not __ldg(): nvcc treats ld.global.nc as speculatable and hoisted a guarded
 // `__ldg(bias + n)` above its `if (bias)` check (observed in SASS; a null bias then faults).
 __device__ __forceinline__ float epi_bias(const Epi& e, int n) {
@@ -64,6 +69,15 @@ __device__ __forceinline__ float epi_bias(const Epi& e, int n) {
 
 __device__ __forceinline__ float epi_apply(const Epi& e, float acc, int m, int n) {
     float v = __fmul_rn(acc, e.sa[(size_t)m * e.sa_stride]);
+    v = __fmul_rn(v, e.sb[(size_t)n * e.sb_stride]);
+    if (e.bias) v = __fadd_rn(v, epi_bias(e, n));
+    if (e.sr) v = __fmul_rn(v, *e.sr);
+    return v;
+}
+
+// same with the row scale supplied by the caller (kernels that quantise the activations themselves)
+__device__ __forceinline__ float epi_apply_sa(const Epi& e, float acc, float sa, int n) {
+    float v = __fmul_rn(acc, sa);
     v = __fmul_rn(v, e.sb[(size_t)n * e.sb_stride]);
     if (e.bias) v = __fadd_rn(v, epi_bias(e, n));
     if (e.sr) v = __fmul_rn(v, *e.sr);

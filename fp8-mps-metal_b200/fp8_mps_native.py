@@ -137,6 +137,20 @@ def fp8_encode(input: torch.Tensor):
     return lib.fp8_encode(inp)
 
 
+def fp8_encode_many(inputs):
+    """`fp8_encode` of a list of tensors (a checkpoint's weights) in ONE launch per input dtype instead of one
+    launch per tensor: the tensors are streamed as a single tile list, so HBM stays saturated across tensor
+    boundaries.  Returns a list of uint8 tensors, bit-identical to ``[fp8_encode(t) for t in inputs]``."""
+    lib = _get_lib()
+    return lib.fp8_encode_many([_to_device(t) for t in inputs])
+
+
+def fp8_dequantize_many(inputs, dtype: torch.dtype = torch.float16):
+    """`fp8_dequantize_to` of a list of uint8 tensors in one launch (unscaled exact cast)."""
+    lib = _get_lib()
+    return lib.fp8_dequantize_many([_to_device(t) for t in inputs], dtype)
+
+
 def fp8_quantize(input: torch.Tensor):
     """
     Float -> FP8 quantization with automatic scaling (reference: fp8_mps_native.py:158-190).
@@ -161,6 +175,27 @@ def fp8_quantize_rowwise(input: torch.Tensor):
     """
     lib = _get_lib()
     return lib.fp8_quantize_rowwise(_to_device(input))
+
+
+def fp8_linear_dynamic(x: torch.Tensor, B: torch.Tensor, scale_b: torch.Tensor, bias=None, out_dtype=None,
+                       single_kernel: bool = False):
+    """
+    Decode-path linear with dynamic activation quantisation fused into the library call (M <= 16):
+
+        q, inv = fp8_quantize(x[m])  per row        (fp8_mps_native.py:158-190)
+        y = ((dec(q) @ dec(B).T) * inv) * scale_b (+ bias) -> out_dtype
+
+    i.e. what a caller of the reference writes as ``q, s = fp8_quantize(x); torch._scaled_mm(q8, w8.t(),
+    scale_a=s, scale_b=...)`` -- five launches and a host sync there.  x: (M,K) float32/float16/bfloat16;
+    B: (N,K) uint8.  Returns (y, inv_scale_a[M]).
+
+    Default plan: a one-CTA-per-row quantise kernel with the GEMV chained behind it by programmatic dependent
+    launch (the GEMV streams its first weights while the rows are quantised).  ``single_kernel=True`` quantises
+    inside every GEMV CTA instead (no scratch buffer; worthwhile for small N only).  Same result bits.
+    """
+    lib = _get_lib()
+    assert B.dtype == torch.uint8 and B.is_contiguous() and x.shape[1] == B.shape[1]
+    return lib.fp8_linear_dynamic(_to_device(x), _to_device(B), scale_b, bias, out_dtype, single_kernel)
 
 
 def fp8_scaled_mm_auto(A: torch.Tensor, B: torch.Tensor,

@@ -116,6 +116,24 @@ FP8B_API int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t n,
 FP8B_API int fp8b_encode(const void* in, int in_dtype, uint8_t* out, size_t n, const float* prescale, void* stream);
 
 /*
+ * Batched casts: many tensors, ONE launch (per 512 tensors).  Converting a checkpoint with the reference is one
+ * Tensor.to() per weight (fp8_mps_patch.py:143-230 -> fp8_mps_native.py:127-155 / :98-124), i.e. one kernel launch
+ * per tensor; on a B200 the ramp-up and drain of a launch cost ~15 % of a FLUX-sized tensor's streaming time.
+ * These entry points take a HOST array of (in, out, n) device spans and stream them as one tile list.
+ *   fp8b_encode_batch : span.in = in_dtype elements, span.out = uint8     (== fp8b_encode with prescale NULL, per span)
+ *   fp8b_dequant_batch: span.in = uint8,             span.out = out_dtype (== fp8b_dequant, per span)
+ * Spans may have any length (0 allowed) and any alignment (unaligned ones take the single-tensor path); they must
+ * not overlap.  The span table is passed in the kernel parameters: nothing is copied, nothing is allocated.
+ */
+typedef struct fp8b_span {
+    const void* in;
+    void* out;
+    size_t n;          /* elements */
+} fp8b_span;
+FP8B_API int fp8b_encode_batch(const fp8b_span* spans, int count, int in_dtype, void* stream);
+FP8B_API int fp8b_dequant_batch(const fp8b_span* spans, int count, int out_dtype, void* stream);
+
+/*
  * amax -> scale, on the device, without the reference's .item() host sync (fp8_mps_native.py:174-176,:189):
  *     amax      = max_i |f32(in[i])|
  *     scale_d   = amax > 0 ? 448.0 / (double)amax : 1.0        (Python-double arithmetic)
@@ -169,6 +187,29 @@ FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out
                    const float* scale_result,
                    void* workspace, size_t workspace_bytes,
                    int algo, void* stream);
+
+/*
+ * Fused  fp8_quantize (per row)  ->  _scaled_mm  for the decode path, M <= 16, in ONE launch:
+ *     q[m,:], inv_m = fp8_quantize(X[m,:])          (amax, 448/amax in double, encode; fp8_mps_native.py:158-190)
+ *     C[m,n] = cast_out( (((sum_k dec(q[m,k]) * dec(B[n,k])) * inv_m) * sb [+ bias[n]]) [* scale_result[0]] )
+ * X is (M,K) float32 / float16 / bfloat16, contiguous.  For M == 1 this is exactly the reference composition
+ * fp8_quantize(x) then torch._scaled_mm(x8, w8.t(), scale_a=inv, ...); for M > 1 each row gets its own scale
+ * (= fp8b_quantize_rows).  The quantised bytes never touch HBM; inv_scale_a_out (device float[M], nullable)
+ * receives the row scales.  Needs K % 16 == 0 and 16-byte aligned X and B, else FP8B_ERR_UNSUPPORTED.
+ *
+ * workspace (device, 16-byte aligned, >= fp8b_gemv_dynamic_workspace_bytes(M,K)) selects the faster plan: the rows
+ * are quantised once into the workspace by a one-CTA-per-row kernel and the GEMV is chained behind it with
+ * programmatic dependent launch, so it is resident and streaming its first weight vectors while the rows are
+ * quantised (two launches, ~one launch of latency).  With workspace == NULL a single kernel quantises inside every
+ * CTA: no scratch memory, but the encode is repeated per CTA, which only pays for small N.  Same bytes either way.
+ * (Replaces four launches of the reference path: .to(f32), abs().max(), multiply, float_to_fp8_kernel, plus the matmul.)
+ */
+FP8B_API int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
+                      int M, int N, int K, int64_t ldc,
+                      const float* scale_b, int scale_b_len,
+                      const void* bias, int bias_dtype, const float* scale_result,
+                      float* inv_scale_a_out, void* workspace, size_t workspace_bytes, void* stream);
+FP8B_API size_t fp8b_gemv_dynamic_workspace_bytes(int M, int K);
 
 FP8B_API size_t fp8b_scaled_mm_workspace_bytes(int M, int N, int K);
 

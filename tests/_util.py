@@ -56,8 +56,30 @@ def capi():
     L.fp8b_scaled_mm_workspace_bytes.argtypes = [i32, i32, i32]
     L.fp8b_scaled_mm_select.restype = i32
     L.fp8b_scaled_mm_select.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64]
+    if hasattr(L, "fp8b_encode_batch") or not os.environ.get("FP8B_LIB"):
+        L.fp8b_encode_batch.restype = i32
+        L.fp8b_encode_batch.argtypes = [vp, i32, i32, vp]
+        L.fp8b_dequant_batch.restype = i32
+        L.fp8b_dequant_batch.argtypes = [vp, i32, i32, vp]
+    if hasattr(L, "fp8b_gemv_dynamic") or not os.environ.get("FP8B_LIB"):   # (an older A/B build may lack it)
+        L.fp8b_gemv_dynamic.restype = i32
+        L.fp8b_gemv_dynamic.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, vp, vp, sz, vp]
+        L.fp8b_gemv_dynamic_workspace_bytes.restype = sz
+        L.fp8b_gemv_dynamic_workspace_bytes.argtypes = [i32, i32]
     _lib = L
     return L
+
+
+class Span(ctypes.Structure):
+    """fp8b_span (include/fp8_b200.h)"""
+    _fields_ = [("inp", ctypes.c_void_p), ("out", ctypes.c_void_p), ("n", ctypes.c_size_t)]
+
+
+def make_spans(triples):
+    arr = (Span * max(1, len(triples)))()
+    for i, (a, b, n) in enumerate(triples):
+        arr[i].inp, arr[i].out, arr[i].n = a, b, n
+    return arr
 
 
 def dt_code(torch_dtype):

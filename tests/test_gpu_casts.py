@@ -7,7 +7,7 @@ import torch
 
 import c_oracle
 import fp8_oracle as o
-from _util import BF16, F16, F32, capi, dt_code, p, stream_ptr, to_np
+from _util import BF16, F16, F32, capi, dt_code, make_spans, p, stream_ptr, to_np
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -221,3 +221,82 @@ def test_full_size_properties():
     rb = _encode_capi(h)
     expect = torch.where(((b & 0x7F) == 0x7F) | (b == 0x80), torch.zeros_like(b), b)
     assert torch.equal(rb, expect)
+
+
+# ------------------------------------------------------------------ batched casts (many tensors, one launch)
+
+def _oracle_encode(x):
+    if x.dtype == torch.bfloat16:
+        return c_oracle.encode_bf16_bits(x.view(torch.int16).numpy().view(np.uint16))
+    return c_oracle.encode(x.numpy())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_batch_casts_ragged_spans(dtype):
+    """fp8b_encode_batch / fp8b_dequant_batch over ragged, empty, sub-vector and MISALIGNED spans carved out of
+    one arena: every span bit-exact against the C oracle, and not a byte written outside the spans."""
+    sizes = [0, 1, 3, 7, 8, 9, 8191, 8192, 8193, 1024 * 8 * 3 + 5, 100003, 1 << 20, 0, 17, (1 << 21) + 11]
+    gaps = [0, 16, 16, 2, 16, 6, 16, 16, 16, 16, 10, 16, 16, 16, 16]     # element gaps: some starts lose 16-B alignment
+    total = sum(sizes) + sum(gaps) + 64
+    g = torch.Generator().manual_seed(123)
+    arena = (torch.randn(total, generator=g) * 3.0).to(dtype)
+    arena[::97] = 0.0
+    arena[5::1013] = -0.0
+    ad = arena.to(DEV)
+    out = torch.full((total,), 0xAB, dtype=torch.uint8, device=DEV)
+    esz = arena.element_size()
+    offs, off = [], 8
+    for n, gap in zip(sizes, gaps):
+        offs.append(off)
+        off += n + gap
+    spans = make_spans([(ad.data_ptr() + esz * o_, out.data_ptr() + o_, n) for o_, n in zip(offs, sizes)])
+    rc = capi().fp8b_encode_batch(spans, len(sizes), dt_code(dtype), stream_ptr())
+    assert rc == 0, capi().fp8b_status_string(rc)
+    got = out.cpu().numpy()
+    expect = np.full(total, 0xAB, dtype=np.uint8)
+    for o_, n in zip(offs, sizes):
+        expect[o_:o_ + n] = _oracle_encode(arena[o_:o_ + n])
+    assert np.array_equal(got, expect)
+
+    for odt in (torch.float16, torch.bfloat16, torch.float32):
+        wide = torch.full((total,), 7.0, dtype=odt, device=DEV)
+        src = torch.from_numpy(expect).to(DEV)
+        spans = make_spans([(src.data_ptr() + o_, wide.data_ptr() + wide.element_size() * o_, n) for o_, n in zip(offs, sizes)])
+        rc = capi().fp8b_dequant_batch(spans, len(sizes), dt_code(odt), stream_ptr())
+        assert rc == 0, capi().fp8b_status_string(rc)
+        w = to_np(wide)
+        ref = np.full(total, 7.0, dtype=np.float32)
+        for o_, n in zip(offs, sizes):
+            ref[o_:o_ + n] = o.decode(expect[o_:o_ + n])
+        assert np.array_equal(w.view(np.uint32), ref.view(np.uint32))
+
+
+def test_batch_casts_many_tensors_python_api():
+    """More tensors than one span table holds (512), mixed dtypes and shapes, through fp8_mps_native."""
+    import fp8_mps_native
+    g = torch.Generator().manual_seed(9)
+    dts = [torch.bfloat16, torch.float16, torch.float32]
+    xs = [(torch.randn(1 + (i * 37) % 300, 1 + (i * 11) % 50, generator=g) * (0.01 + i % 7)).to(dts[i % 3]) for i in range(1100)]
+    xs.append(torch.empty(0, 4, dtype=torch.bfloat16))
+    qs = fp8_mps_native.fp8_encode_many([x.to(DEV) for x in xs])
+    assert len(qs) == len(xs)
+    for x, q in zip(xs, qs):
+        assert q.shape == x.shape and q.dtype == torch.uint8
+        assert np.array_equal(q.cpu().numpy().reshape(-1), _oracle_encode(x.reshape(-1)))
+    ws = fp8_mps_native.fp8_dequantize_many(qs, torch.bfloat16)
+    for q, w in zip(qs, ws):
+        assert w.shape == q.shape and w.dtype == torch.bfloat16
+        assert np.array_equal(to_np(w).reshape(-1).view(np.uint32), o.decode(q.cpu().numpy().reshape(-1)).view(np.uint32))
+    assert fp8_mps_native.fp8_encode_many([]) == []
+
+
+def test_batch_casts_validation():
+    L = capi()
+    x = torch.zeros(16, dtype=torch.bfloat16, device=DEV)
+    q = torch.zeros(16, dtype=torch.uint8, device=DEV)
+    assert L.fp8b_encode_batch(None, 0, BF16, stream_ptr()) == 0
+    assert L.fp8b_encode_batch(None, 2, BF16, stream_ptr()) == -1
+    assert L.fp8b_encode_batch(make_spans([(x.data_ptr(), q.data_ptr(), 16)]), 1, 9, stream_ptr()) == -1
+    assert L.fp8b_encode_batch(make_spans([(None, q.data_ptr(), 16)]), 1, BF16, stream_ptr()) == -1
+    assert L.fp8b_dequant_batch(make_spans([(q.data_ptr(), None, 4)]), 1, F16, stream_ptr()) == -1
+    assert L.fp8b_dequant_batch(make_spans([(None, None, 0)]), 1, F16, stream_ptr()) == 0

@@ -365,3 +365,88 @@ def test_capi_argument_validation():
     assert L.fp8b_status_string(-2).startswith(b"unsupported")
     rc, out = mm_capi(A[:0], B, one, one)                         # M == 0 is a valid empty problem
     assert rc == 0 and out.shape == (0, 8)
+
+
+@pytest.mark.parametrize("M,K,N,xdt,odt,kw", [
+    (1, 14336, 4096, torch.bfloat16, torch.bfloat16, {}),
+    (1, 4096, 512, torch.float32, None, {"bias": True}),
+    (4, 4096, 300, torch.float16, torch.float16, {"per_row_b": True}),
+    (7, 2048, 64, torch.bfloat16, None, {}),                      # two passes of <= 4 rows, cluster split-K
+    (16, 512, 40, torch.float32, torch.bfloat16, {"bias": True, "per_row_b": True}),
+    (1, 100000, 24, torch.float32, None, {}),                     # K panel loop
+    (2, 100000, 24, torch.float32, None, {"tol": 3e-5}),         # tensor-core accumulation over a long K
+])
+@pytest.mark.parametrize("single", [False, True])
+def test_fused_dynamic_quantize_gemv(M, K, N, xdt, odt, kw, single):
+    """fp8_linear_dynamic == the reference composition fp8_quantize(x) per row -> _scaled_mm, in one launch.
+    The quantised activations must be the oracle's bytes exactly, so the only difference from the oracle result
+    is fp32 summation order."""
+    import fp8_mps_native
+    g = torch.Generator().manual_seed(M * 13 + N)
+    x = (torch.randn(M, K, generator=g) * (torch.rand(M, 1, generator=g) * 5 + 0.1)).to(xdt)
+    if M > 2:
+        x[2].zero_()                                              # amax == 0 -> scale 1.0
+    W = _rand_fp8((N, K), M + K)
+    sb = (np.random.default_rng(N).random(N if kw.get("per_row_b") else 1).astype(np.float32) + 0.5) * 0.02
+    bias = torch.randn(N, generator=g).to(odt or torch.float32) if kw.get("bias") else None
+    y, inv = fp8_mps_native.fp8_linear_dynamic(x.to(DEV), torch.from_numpy(W).to(DEV), torch.from_numpy(sb),
+                                               None if bias is None else bias.to(DEV), odt, single_kernel=single)
+    assert y.shape == (M, N) and y.dtype == (odt or torch.float32) and inv.shape == (M,)
+    qs, invs = zip(*[o.fp8_quantize(x[m].float().numpy()) for m in range(M)])
+    q = np.stack(qs)
+    inv_ref = np.concatenate(invs)
+    assert np.array_equal(inv.cpu().numpy().view(np.uint32), inv_ref.view(np.uint32))
+    ref = o.scaled_mm(q, W, inv_ref, sb, None if bias is None else to_np(bias), None, dt_name(odt))
+    _check(y, ref, odt, tol=kw.get("tol"), what=f"fused dynamic M{M} K{K} N{N}")
+    # and it equals the two-step path of this library bit for bit in the quantised operands
+    q2, inv2 = fp8_mps_native.fp8_quantize_rowwise(x.to(DEV))
+    assert np.array_equal(q2.cpu().numpy(), q)
+
+
+@pytest.mark.parametrize("M", [1, 2, 12])
+def test_pdl_chain_sees_fresh_activations(M):
+    """Programmatic dependent launch regression: the GEMV is resident BEFORE its predecessor has written the
+    activations, so every activation load must come after griddepcontrol.wait (a non-coherent load was hoisted
+    above it once and read the previous call's bytes).  x is regenerated on the device right before each call and
+    the workspace address is reused, so a stale read changes the result."""
+    import fp8_mps_native
+    K, N = 8192, 96
+    g = torch.Generator(device=DEV).manual_seed(5)
+    W = torch.from_numpy(_rand_fp8((N, K), 3)).to(DEV)
+    sb = torch.tensor([0.02], device=DEV)
+    for it in range(40):
+        x = torch.randn(M, K, device=DEV, generator=g) * (1.0 + it)        # written by the kernel just before
+        y, inv = fp8_mps_native.fp8_linear_dynamic(x, W, sb, None, None)
+        q, inv2 = fp8_mps_native.fp8_quantize_rowwise(x)
+        torch.cuda.synchronize()
+        ref = fp8_mps_native.fp8_scaled_mm_fused(q, W, inv2, sb, None, None, None)   # no PDL on this path
+        torch.cuda.synchronize()
+        assert torch.equal(inv, inv2)
+        assert torch.equal(y, ref), f"iteration {it}: chained result differs from the unchained one"
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_static_weights_option_sees_fresh_activations(M):
+    """Same hazard through FP8B_OPT_STATIC_WEIGHTS: only B may be read before the wait."""
+    import fp8_mps_native
+    K, N = 8192, 96
+    W = torch.from_numpy(_rand_fp8((N, K), 7)).to(DEV)
+    base = torch.from_numpy(_rand_fp8((M, K), 8)).to(DEV)
+    sa = torch.tensor([0.5], device=DEV); sb = torch.tensor([0.02], device=DEV)
+    refs = []
+    for it in range(24):
+        x = torch.roll(base, it, dims=1).contiguous()
+        refs.append(fp8_mps_native.fp8_scaled_mm_fused(x, W, sa, sb, None, None, None))
+    torch.cuda.synchronize()
+    fp8_mps_native.set_static_weights(True)
+    try:
+        buf = torch.empty_like(base)
+        outs = []
+        for it in range(24):
+            buf.copy_(torch.roll(base, it, dims=1))                          # predecessor writes the activations
+            outs.append(fp8_mps_native.fp8_scaled_mm_fused(buf, W, sa, sb, None, None, None))
+        torch.cuda.synchronize()
+    finally:
+        fp8_mps_native.set_static_weights(False)
+    for it in range(24):
+        assert torch.equal(outs[it], refs[it]), f"iteration {it}"
