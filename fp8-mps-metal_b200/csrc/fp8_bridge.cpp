@@ -11,6 +11,8 @@
 // waitUntilCompleted (fp8_bridge.cpp:180-185,244-245), this one passes device pointers and the
 // caller's current CUDA stream and returns without synchronising.  No CUDA kernel lives here and
 // nothing falls back to ATen math: every op is one or two calls into the C ABI.
+#include <stdexcept>
+#include <string>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -27,15 +29,19 @@ int to_fp8b_dtype(at::ScalarType t)
         case at::kFloat: return FP8B_F32;
         case at::kHalf: return FP8B_F16;
         case at::kBFloat16: return FP8B_BF16;
-        default: TORCH_CHECK(false, "fp8_metal: unsupported dtype ", t, " (need float32, float16 or bfloat16)");
+        default: throw std::runtime_error(std::string("fp8_metal: unsupported dtype ") + c10::toString(t) +
+                                          " (need float32, float16 or bfloat16)");
     }
     return -1;
 }
 
+// The reference raises std::runtime_error for launch failures (fp8_bridge.cpp:96-101); so does this.
 void check_status(int rc, const char* what)
 {
-    TORCH_CHECK(rc == FP8B_OK, "fp8_metal: ", what, " failed: ", fp8b_status_string(rc),
-                " (status ", rc, ", cuda error ", fp8b_last_cuda_error(), ")");
+    if (rc == FP8B_OK) return;
+    std::string msg = std::string("fp8_metal: ") + what + " failed: " + fp8b_status_string(rc) + " (status " +
+                      std::to_string(rc) + ", cuda error " + std::to_string(fp8b_last_cuda_error()) + ")";
+    throw std::runtime_error(msg);
 }
 
 void* current_stream() { return static_cast<void*>(at::cuda::getCurrentCUDAStream().stream()); }
@@ -279,7 +285,7 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_quantize_rowwise(torch::Tensor inpu
     return std::make_tuple(out, inv);
 }
 
-// Fused per-row fp8_quantize(x) -> scaled matmul for M <= 16 (decode path): x is float, B is uint8 (N,K).
+// Per-row fp8_quantize(x) -> scaled matmul in one library call (any M): x is float, B is uint8 (N,K).
 // Returns (C, inv_scale_a[M]).
 std::tuple<torch::Tensor, torch::Tensor> fp8_linear_dynamic(torch::Tensor x, torch::Tensor B, torch::Tensor scale_b,
                                                             c10::optional<torch::Tensor> bias,
@@ -315,14 +321,14 @@ std::tuple<torch::Tensor, torch::Tensor> fp8_linear_dynamic(torch::Tensor x, tor
     void* ws_ptr = nullptr;
     size_t ws_bytes = 0;
     if (!single_kernel) {
-        ws_bytes = fp8b_gemv_dynamic_workspace_bytes((int)M, (int)K);
+        ws_bytes = fp8b_linear_dynamic_workspace_bytes((int)M, (int)K);
         ws = torch::empty({(int64_t)ws_bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(x.device()));
         ws_ptr = ws.data_ptr();
     }
-    int rc = fp8b_gemv_dynamic(xin.data_ptr(), to_fp8b_dtype(xin.scalar_type()), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt),
+    int rc = fp8b_linear_dynamic(xin.data_ptr(), to_fp8b_dtype(xin.scalar_type()), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt),
                                (int)M, (int)N, (int)K, N, sb.data_ptr<float>(), (int)sb.numel(), bias_ptr, bias_dt, nullptr,
                                inv.data_ptr<float>(), ws_ptr, ws_bytes, current_stream());
-    check_status(rc, "fp8b_gemv_dynamic");
+    check_status(rc, "fp8b_linear_dynamic");
     return std::make_tuple(C, inv);
 }
 
@@ -342,7 +348,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("fp8_dequantize", &fp8_dequantize, "FP8 to float16 dequantization on the GPU",
           py::arg("input"), py::arg("scale"));
     m.def("fp8_quantize", &fp8_quantize, "Float to FP8 quantization on the GPU", py::arg("input"));
-    m.def("fp8_linear_dynamic", &fp8_linear_dynamic, "Fused per-row quantize + FP8 matmul for M <= 16",
+    m.def("fp8_linear_dynamic", &fp8_linear_dynamic, "Per-row dynamic quantize + FP8 matmul in one call",
           py::arg("x"), py::arg("B"), py::arg("scale_b"), py::arg("bias") = py::none(), py::arg("out_dtype") = py::none(),
           py::arg("single_kernel") = false);
     m.def("fp8_quantize_rowwise", &fp8_quantize_rowwise, "Per-row float to FP8 quantization", py::arg("input"));

@@ -160,13 +160,13 @@ extern "C" int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
-extern "C" size_t fp8b_gemv_dynamic_workspace_bytes(int M, int K)
+extern "C" size_t fp8b_linear_dynamic_workspace_bytes(int M, int K)
 {
     if (M <= 0 || K <= 0) return 0;
     return align16((size_t)M * (size_t)K) + align16((size_t)M * sizeof(float));
 }
 
-extern "C" int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
+extern "C" int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
                                  int M, int N, int K, int64_t ldc,
                                  const float* scale_b, int scale_b_len,
                                  const void* bias, int bias_dtype, const float* scale_result,
@@ -178,7 +178,10 @@ extern "C" int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, v
     if (bias && !valid_dtype(bias_dtype)) return FP8B_ERR_INVALID;
     if (ldc < N || !(scale_b_len == 1 || scale_b_len == N)) return FP8B_ERR_INVALID;
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
-    if (M > 16 || K < 16 || (K % 16) != 0 || !aligned(B, 16) || !aligned(X, 16)) return FP8B_ERR_UNSUPPORTED;
+    const size_t need = fp8b_linear_dynamic_workspace_bytes(M, K);
+    const bool have_ws = workspace && workspace_bytes >= need && aligned(workspace, 16);
+    if (M <= 16 && (K < 16 || (K % 16) != 0 || !aligned(B, 16) || !aligned(X, 16))) return FP8B_ERR_UNSUPPORTED;
+    if (M > 16 && !have_ws) return FP8B_ERR_UNSUPPORTED;         // the GEMM path always quantises into the workspace
     MMArgs a;
     a.A = nullptr; a.B = B; a.C = C; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
     a.sa = scale_b; a.sa_len = 1;                 // replaced below / unused by the single-kernel path
@@ -190,15 +193,21 @@ extern "C" int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, v
     // programmatic dependent launch -- the GEMV is resident and already streaming its first weight vectors
     // while the rows are quantised.  Without: one kernel in which every CTA quantises the rows it needs
     // (cheaper only when the grid is small; it repeats the encode per CTA).
-    const size_t need = fp8b_gemv_dynamic_workspace_bytes(M, K);
+    // M > 16: the same quantise kernel, then the shape-selected GEMM (tcgen05 when TMA-able) with per-row
+    // scale_a.  Converting inside the GEMM's producer stage instead would redo the encode once per N-tile
+    // column (48x for C4) on data that is read from L2 anyway; one 6 us pass over A is cheaper.
     const int plan = tune_int("FP8B_DYNAMIC_PLAN", 0);         // 1 = force single kernel, 2 = force chain
-    if (workspace && workspace_bytes >= need && aligned(workspace, 16) && plan != 1) {
+    if (have_ws && (plan != 1 || M > 16)) {
         uint8_t* q = static_cast<uint8_t*>(workspace);
         float* inv = inv_scale_a_out ? inv_scale_a_out
                                      : reinterpret_cast<float*>(q + align16((size_t)M * (size_t)K));
         int rc = fp8b_quantize_rows(X, x_dtype, M, (size_t)K, q, inv, stream);
         if (rc != FP8B_OK) return rc;
         a.A = q; a.sa = inv; a.sa_len = M;
+        if (M > 16) {
+            const int algo = select_algo(a);
+            return algo == FP8B_MM_TCGEN05 ? launch_gemm_tcgen05(a) : algo == FP8B_MM_GEMV ? launch_gemv(a) : launch_gemm_simt(a);
+        }
         a.chain_pdl = 1;
         return launch_gemv(a);
     }

@@ -330,7 +330,7 @@ quantize_rows_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, flo
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     constexpr int ESZ = (IN == FP8B_F32) ? 4 : 2;
-    pdl_launch_dependents();             // fp8b_gemv_dynamic chains a GEMV behind this kernel (it waits before reading out)
+    pdl_launch_dependents();             // fp8b_linear_dynamic chains a GEMV behind this kernel (it waits before reading out)
     const size_t row = blockIdx.x;
     const uint8_t* rin = reinterpret_cast<const uint8_t*>(in) + row * cols * ESZ;
     uint8_t* rout = out + row * cols;

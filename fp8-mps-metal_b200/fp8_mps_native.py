@@ -180,7 +180,7 @@ def fp8_quantize_rowwise(input: torch.Tensor):
 def fp8_linear_dynamic(x: torch.Tensor, B: torch.Tensor, scale_b: torch.Tensor, bias=None, out_dtype=None,
                        single_kernel: bool = False):
     """
-    Decode-path linear with dynamic activation quantisation fused into the library call (M <= 16):
+    Linear layer with dynamic per-row activation quantisation in one library call, no host sync (any M):
 
         q, inv = fp8_quantize(x[m])  per row        (fp8_mps_native.py:158-190)
         y = ((dec(q) @ dec(B).T) * inv) * scale_b (+ bias) -> out_dtype
@@ -189,9 +189,9 @@ def fp8_linear_dynamic(x: torch.Tensor, B: torch.Tensor, scale_b: torch.Tensor, 
     scale_a=s, scale_b=...)`` -- five launches and a host sync there.  x: (M,K) float32/float16/bfloat16;
     B: (N,K) uint8.  Returns (y, inv_scale_a[M]).
 
-    Default plan: a one-CTA-per-row quantise kernel with the GEMV chained behind it by programmatic dependent
-    launch (the GEMV streams its first weights while the rows are quantised).  ``single_kernel=True`` quantises
-    inside every GEMV CTA instead (no scratch buffer; worthwhile for small N only).  Same result bits.
+    Default plan: a one-CTA-per-row quantise kernel, then the GEMV (M <= 16, chained by programmatic dependent
+    launch) or the tcgen05 GEMM (M > 16) with per-row scale_a.  ``single_kernel=True`` (M <= 16 only) quantises
+    inside every GEMV CTA instead: no scratch buffer, worthwhile for small N only.  Same result bits.
     """
     lib = _get_lib()
     assert B.dtype == torch.uint8 and B.is_contiguous() and x.shape[1] == B.shape[1]

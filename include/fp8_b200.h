@@ -189,27 +189,29 @@ FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out
                    int algo, void* stream);
 
 /*
- * Fused  fp8_quantize (per row)  ->  _scaled_mm  for the decode path, M <= 16, in ONE launch:
+ * Linear layer with DYNAMIC per-row activation quantisation: fp8_quantize (per row) -> _scaled_mm in one call,
+ * no host synchronisation (the reference's fp8_quantize reads amax back with .item(), fp8_mps_native.py:174):
  *     q[m,:], inv_m = fp8_quantize(X[m,:])          (amax, 448/amax in double, encode; fp8_mps_native.py:158-190)
  *     C[m,n] = cast_out( (((sum_k dec(q[m,k]) * dec(B[n,k])) * inv_m) * sb [+ bias[n]]) [* scale_result[0]] )
  * X is (M,K) float32 / float16 / bfloat16, contiguous.  For M == 1 this is exactly the reference composition
  * fp8_quantize(x) then torch._scaled_mm(x8, w8.t(), scale_a=inv, ...); for M > 1 each row gets its own scale
- * (= fp8b_quantize_rows).  The quantised bytes never touch HBM; inv_scale_a_out (device float[M], nullable)
- * receives the row scales.  Needs K % 16 == 0 and 16-byte aligned X and B, else FP8B_ERR_UNSUPPORTED.
+ * (= fp8b_quantize_rows).  inv_scale_a_out (device float[M], nullable) receives the row scales.
  *
- * workspace (device, 16-byte aligned, >= fp8b_gemv_dynamic_workspace_bytes(M,K)) selects the faster plan: the rows
- * are quantised once into the workspace by a one-CTA-per-row kernel and the GEMV is chained behind it with
- * programmatic dependent launch, so it is resident and streaming its first weight vectors while the rows are
- * quantised (two launches, ~one launch of latency).  With workspace == NULL a single kernel quantises inside every
- * CTA: no scratch memory, but the encode is repeated per CTA, which only pays for small N.  Same bytes either way.
- * (Replaces four launches of the reference path: .to(f32), abs().max(), multiply, float_to_fp8_kernel, plus the matmul.)
+ * workspace: device, 16-byte aligned, >= fp8b_linear_dynamic_workspace_bytes(M,K).
+ *   M <= 16, workspace given : rows quantised once by a one-CTA-per-row kernel, the GEMV chained behind it with
+ *                              programmatic dependent launch (two launches).  The default plan of the bindings.
+ *   M <= 16, workspace NULL  : ONE kernel, every CTA quantises the rows itself -- no scratch memory, but the encode
+ *                              is repeated per CTA, so it only pays for small N.  Needs K % 16 == 0 and 16-byte
+ *                              aligned X and B, else FP8B_ERR_UNSUPPORTED.  Same result bits as the chained plan.
+ *   M  > 16                  : workspace required (FP8B_ERR_UNSUPPORTED without); quantise kernel, then the GEMM
+ *                              fp8b_scaled_mm would pick, with per-row scale_a.
  */
-FP8B_API int fp8b_gemv_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
+FP8B_API int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B, void* C, int out_dtype,
                       int M, int N, int K, int64_t ldc,
                       const float* scale_b, int scale_b_len,
                       const void* bias, int bias_dtype, const float* scale_result,
                       float* inv_scale_a_out, void* workspace, size_t workspace_bytes, void* stream);
-FP8B_API size_t fp8b_gemv_dynamic_workspace_bytes(int M, int K);
+FP8B_API size_t fp8b_linear_dynamic_workspace_bytes(int M, int K);
 
 FP8B_API size_t fp8b_scaled_mm_workspace_bytes(int M, int N, int K);
 

@@ -61,11 +61,11 @@ def capi():
         L.fp8b_encode_batch.argtypes = [vp, i32, i32, vp]
         L.fp8b_dequant_batch.restype = i32
         L.fp8b_dequant_batch.argtypes = [vp, i32, i32, vp]
-    if hasattr(L, "fp8b_gemv_dynamic") or not os.environ.get("FP8B_LIB"):   # (an older A/B build may lack it)
-        L.fp8b_gemv_dynamic.restype = i32
-        L.fp8b_gemv_dynamic.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, vp, vp, sz, vp]
-        L.fp8b_gemv_dynamic_workspace_bytes.restype = sz
-        L.fp8b_gemv_dynamic_workspace_bytes.argtypes = [i32, i32]
+    if hasattr(L, "fp8b_linear_dynamic") or not os.environ.get("FP8B_LIB"):   # (an older A/B build may lack it)
+        L.fp8b_linear_dynamic.restype = i32
+        L.fp8b_linear_dynamic.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, vp, vp, sz, vp]
+        L.fp8b_linear_dynamic_workspace_bytes.restype = sz
+        L.fp8b_linear_dynamic_workspace_bytes.argtypes = [i32, i32]
     _lib = L
     return L
 

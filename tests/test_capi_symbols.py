@@ -72,3 +72,18 @@ def test_compute_entry_points_fail_loudly_without_a_device():
     # empty problems are accepted and do nothing
     assert L.fp8b_encode(None, 0, None, 0, None, None) == 0
     assert L.fp8b_scaled_mm(None, None, None, 0, 0, 4, 16, 4, None, 1, None, 1, None, 0, None, None, 0, 0, None) == 0
+
+
+def test_bridge_errors_are_python_exceptions():
+    """Failures inside the torch extension surface as RuntimeError (the reference raises std::runtime_error /
+    TORCH_CHECK, fp8_bridge.cpp:96-101,174-177) -- including the ones with a formatted message, which once took
+    the interpreter down."""
+    import pytest
+    import torch
+    import fp8_metal
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        fp8_metal.set_option(99, 1)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        fp8_metal.fp8_dequantize(torch.zeros(4, dtype=torch.uint8), torch.ones(1))
+    with pytest.raises(RuntimeError, match="uint8"):
+        fp8_metal.fp8_dequantize(torch.zeros(4, dtype=torch.int32), torch.ones(1))

@@ -450,3 +450,24 @@ def test_static_weights_option_sees_fresh_activations(M):
         fp8_mps_native.set_static_weights(False)
     for it in range(24):
         assert torch.equal(outs[it], refs[it]), f"iteration {it}"
+
+
+@pytest.mark.parametrize("M,K,N,xdt,odt", [(64, 1024, 512, torch.bfloat16, torch.bfloat16),
+                                           (300, 2048, 384, torch.float16, None),
+                                           (17, 4096, 256, torch.float32, torch.float16)])
+def test_dynamic_linear_large_m(M, K, N, xdt, odt):
+    """M > 16: per-row quantise + tcgen05 GEMM with per-row scale_a, against the oracle composition."""
+    import fp8_mps_native
+    g = torch.Generator().manual_seed(M + N)
+    x = (torch.randn(M, K, generator=g) * (torch.rand(M, 1, generator=g) * 4 + 0.05)).to(xdt)
+    W = _rand_fp8((N, K), K + 1)
+    sb = (np.random.default_rng(N).random(N).astype(np.float32) + 0.5) * 0.02
+    bias = torch.randn(N, generator=g)
+    y, inv = fp8_mps_native.fp8_linear_dynamic(x.to(DEV), torch.from_numpy(W).to(DEV), torch.from_numpy(sb), bias.to(DEV), odt)
+    qs, invs = zip(*[o.fp8_quantize(x[m].float().numpy()) for m in range(M)])
+    inv_ref = np.concatenate(invs)
+    assert np.array_equal(inv.cpu().numpy().view(np.uint32), inv_ref.view(np.uint32))
+    ref = o.scaled_mm(np.stack(qs), W, inv_ref, sb, to_np(bias), None, dt_name(odt))
+    _check(y, ref, odt, what=f"dynamic linear M{M}")
+    with pytest.raises(RuntimeError):
+        fp8_mps_native.fp8_linear_dynamic(x.to(DEV), torch.from_numpy(W).to(DEV), torch.from_numpy(sb), None, odt, single_kernel=True)
