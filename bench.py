@@ -30,6 +30,7 @@ threads), same JSON shape with "impl": "reference".
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes
 import json
 import os
@@ -580,7 +581,8 @@ def main():
     per_gpu = value / n_gpus
 
     # ---------------- e2e: patched torch._scaled_mm with pinned HOST buffers, copies inside the timed region
-    fp8_mps_patch.install()
+    with contextlib.redirect_stdout(sys.stderr):      # install() prints like the reference; stdout carries the JSON line only
+        fp8_mps_patch.install()
     try:
         hx = x.cpu().pin_memory()
         hW = Ws[0].cpu().pin_memory()

@@ -16,20 +16,23 @@ namespace fp8b {
 
 constexpr int kCastThreads = 256;
 
+// Streaming loads.  Deliberately NOT .nc: the tile kernels run under programmatic dependent launch (resident before
+// their predecessor has finished), and ptxas moves non-coherent loads above griddepcontrol.wait (seen in the
+// GEMV kernels' SASS); a coherent load stays behind it.
 __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
     uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
 __device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
     uint32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
 __device__ __forceinline__ void stg_stream_v4(void* p, uint4 v) {
@@ -41,6 +44,13 @@ __device__ __forceinline__ void stg_stream_v2(void* p, uint2 v) {
 }
 __device__ __forceinline__ void stg_stream_u32(void* p, uint32_t v) {
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// the optional scale / prescale scalar is typically written by the kernel just before (amax_finalize_kernel)
+__device__ __forceinline__ float ld_scalar_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
 }
 
 __device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
@@ -56,12 +66,30 @@ __device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
 // bytes per load).  Launch shapes are chosen on the host (cast_shape below): measured on B200, copy-like
 // kernels peak with ~4096 wide vectors (64 KB) in flight per SM and LOSE bandwidth beyond that.
 
+// How one CTA of a single-tensor launch walks its tensor: `rounds` full rounds of gridDim.x tiles (CTA b takes tile
+// r * gridDim.x + b), then the remaining < gridDim.x tiles' worth of vectors is cut into gridDim.x equal
+// contiguous shares (512-byte granules), so every CTA finishes at the same time instead of a third of the SMs
+// idling through a last partial round.
+template <int TILE>
+struct TileWalk {
+    size_t rounds, rem_begin, rem_end;
+    __device__ __forceinline__ explicit TileWalk(size_t nvec) {
+        const size_t per_round = (size_t)gridDim.x * TILE;
+        rounds = nvec / per_round;
+        const size_t base = rounds * per_round;
+        const size_t granules = (nvec - base + 31) / 32;
+        const size_t share = (granules + gridDim.x - 1) / gridDim.x * 32;      // <= TILE because nvec - base < per_round
+        rem_begin = base + blockIdx.x * share;
+        rem_end = rem_begin + share < nvec ? rem_begin + share : nvec;
+    }
+};
+
 // FP8 -> wide.  OUT: FP8B_F16 / FP8B_BF16 / FP8B_F32.  SCALED (f16 only): fp16 multiply by RN16(scale).
 template <int OUT, bool SCALED, int THREADS, int UNROLL>
-__device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t nvec,
-                                            size_t tile, uint32_t s2)
+__device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t vbegin,
+                                            size_t nvec, uint32_t s2)
 {
-    const size_t v0 = tile * (size_t)(THREADS * UNROLL) + threadIdx.x;
+    const size_t v0 = vbegin + threadIdx.x;                    // converts vectors [vbegin, min(vbegin + tile, nvec))
     uint2 w[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -112,7 +140,7 @@ __device__ __forceinline__ void decode_tail(const uint8_t* in, void* out, size_t
         else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
         else {
             __half h = __float2half_rn(f);
-            if (SCALED) h = __hmul(h, __float2half_rn(__ldg(scale)));
+            if (SCALED) h = __hmul(h, __float2half_rn(ld_scalar_f32(scale)));
             reinterpret_cast<__half*>(out)[i] = h;
         }
     }
@@ -125,14 +153,18 @@ fp8_to_wide_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_
 {
     constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;            // elements per 16-byte vector
     const size_t nvec = n / EPV;
-    const size_t ntiles = (nvec + THREADS * UNROLL - 1) / (THREADS * UNROLL);
+    pdl_launch_dependents();          // resident early, idle until the predecessor has completed and flushed
+    pdl_wait();
     uint32_t s2 = 0;
     if (SCALED) {
-        __half2 s = __float2half2_rn(__ldg(scale));           // RN16(scale), native.py:121
+        __half2 s = __float2half2_rn(ld_scalar_f32(scale));   // RN16(scale), native.py:121
         s2 = *reinterpret_cast<uint32_t*>(&s);
     }
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)
-        decode_tile<OUT, SCALED, THREADS, UNROLL>(in, reinterpret_cast<uint8_t*>(out), nvec, t, s2);
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
+    TileWalk<THREADS * UNROLL> walk(nvec);
+    for (size_t r = 0; r < walk.rounds; ++r)
+        decode_tile<OUT, SCALED, THREADS, UNROLL>(in, o8, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s2);
+    if (walk.rem_begin < walk.rem_end) decode_tile<OUT, SCALED, THREADS, UNROLL>(in, o8, walk.rem_begin, walk.rem_end, s2);
     if (blockIdx.x == 0 && threadIdx.x == 0) decode_tail<OUT, SCALED>(in, out, nvec * EPV, n, scale);
 }
 
@@ -197,10 +229,10 @@ __device__ __forceinline__ float load_wide_scalar(const void* in, size_t i) {
 }
 
 template <int IN, bool PRESCALE, int THREADS, int UNROLL>
-__device__ __forceinline__ void encode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t nvec,
-                                            size_t tile, float s)
+__device__ __forceinline__ void encode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t vbegin,
+                                            size_t nvec, float s)
 {
-    const size_t v0 = tile * (size_t)(THREADS * UNROLL) + threadIdx.x;
+    const size_t v0 = vbegin + threadIdx.x;                    // converts vectors [vbegin, min(vbegin + tile, nvec))
     uint4 w[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -226,10 +258,14 @@ wide_to_fp8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const size_t nvec = n / EPV;
-    const size_t ntiles = (nvec + THREADS * UNROLL - 1) / (THREADS * UNROLL);
-    const float s = PRESCALE ? __ldg(prescale) : 1.0f;
-    for (size_t t = blockIdx.x; t < ntiles; t += gridDim.x)
-        encode_tile<IN, PRESCALE, THREADS, UNROLL>(reinterpret_cast<const uint8_t*>(in), out, nvec, t, s);
+    pdl_launch_dependents();
+    pdl_wait();
+    const float s = PRESCALE ? ld_scalar_f32(prescale) : 1.0f;
+    const uint8_t* i8 = reinterpret_cast<const uint8_t*>(in);
+    TileWalk<THREADS * UNROLL> walk(nvec);
+    for (size_t r = 0; r < walk.rounds; ++r)
+        encode_tile<IN, PRESCALE, THREADS, UNROLL>(i8, out, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s);
+    if (walk.rem_begin < walk.rem_end) encode_tile<IN, PRESCALE, THREADS, UNROLL>(i8, out, walk.rem_begin, walk.rem_end, s);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = nvec * EPV; i < n; ++i) {
             float f = load_wide_scalar<IN>(in, i);
@@ -263,19 +299,28 @@ amax_kernel(const void* __restrict__ in, size_t n, uint32_t* __restrict__ amax_b
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const size_t nvec = n / EPV;
+    constexpr int UNROLL = 4;                                  // independent 16-byte loads in flight per thread
     const size_t stride = (size_t)gridDim.x * kCastThreads;
     uint32_t m = 0;
-    for (size_t v = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v < nvec; v += stride) {
-        uint4 w = ldg_stream_v4(reinterpret_cast<const uint8_t*>(in) + v * 16);
-        const uint32_t* p = &w.x;
+    for (size_t v0 = (size_t)blockIdx.x * kCastThreads + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
+        uint4 w[UNROLL];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (IN == FP8B_F32) m = max(m, p[j] & 0x7FFFFFFFu);
-            else if (IN == FP8B_BF16) { m = max(m, (p[j] << 16) & 0x7FFFFFFFu); m = max(m, p[j] & 0x7FFF0000u); }
-            else {
-                float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
-                m = max(m, __float_as_uint(t.x) & 0x7FFFFFFFu);
-                m = max(m, __float_as_uint(t.y) & 0x7FFFFFFFu);
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            w[u] = v < nvec ? ldg_stream_v4(reinterpret_cast<const uint8_t*>(in) + v * 16) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t* p = &w[u].x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (IN == FP8B_F32) m = max(m, p[j] & 0x7FFFFFFFu);
+                else if (IN == FP8B_BF16) { m = max(m, (p[j] << 16) & 0x7FFFFFFFu); m = max(m, p[j] & 0x7FFF0000u); }
+                else {
+                    float2 t = __half22float2(*reinterpret_cast<const __half2*>(&p[j]));
+                    m = max(m, __float_as_uint(t.x) & 0x7FFFFFFFu);
+                    m = max(m, __float_as_uint(t.y) & 0x7FFFFFFFu);
+                }
             }
         }
     }
@@ -399,6 +444,8 @@ template <int IN, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 wide_to_fp8_batch_kernel(const __grid_constant__ CastBatch b)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const uint32_t total = b.tile_end[b.count - 1];
     int span = 0;
@@ -408,7 +455,7 @@ wide_to_fp8_batch_kernel(const __grid_constant__ CastBatch b)
         const size_t n = b.n[span];
         const uint8_t* in = reinterpret_cast<const uint8_t*>(b.in[span]);
         uint8_t* out = reinterpret_cast<uint8_t*>(b.out[span]);
-        encode_tile<IN, false, THREADS, UNROLL>(in, out, n / EPV, t - t0, 1.0f);
+        encode_tile<IN, false, THREADS, UNROLL>(in, out, (size_t)(t - t0) * (THREADS * UNROLL), n / EPV, 1.0f);
         if (t + 1 == b.tile_end[span] && threadIdx.x == 0)    // ragged tail of this tensor (< EPV elements)
             for (size_t i = n / EPV * EPV; i < n; ++i) out[i] = enc1_f32(load_wide_scalar<IN>(in, i));
     }
@@ -418,6 +465,8 @@ template <int OUT, int THREADS, int UNROLL>
 __global__ void __launch_bounds__(THREADS)
 fp8_to_wide_batch_kernel(const __grid_constant__ CastBatch b)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
     const uint32_t total = b.tile_end[b.count - 1];
     int span = 0;
@@ -427,7 +476,7 @@ fp8_to_wide_batch_kernel(const __grid_constant__ CastBatch b)
         const size_t n = b.n[span];
         const uint8_t* in = reinterpret_cast<const uint8_t*>(b.in[span]);
         uint8_t* out = reinterpret_cast<uint8_t*>(b.out[span]);
-        decode_tile<OUT, false, THREADS, UNROLL>(in, out, n / EPV, t - t0, 0u);
+        decode_tile<OUT, false, THREADS, UNROLL>(in, out, (size_t)(t - t0) * (THREADS * UNROLL), n / EPV, 0u);
         if (t + 1 == b.tile_end[span] && threadIdx.x == 0) decode_tail<OUT, false>(in, out, n / EPV * EPV, n, nullptr);
     }
 }
@@ -468,9 +517,9 @@ static int launch_decode_vec(const uint8_t* in, void* out, size_t n, const float
 {
     constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
     const CastShape c = cast_shape(n / EPV);
-    if (c.big) fp8_to_wide_kernel<OUT, SCALED, 512, 8><<<c.grid, 512, 0, st>>>(in, out, n, scale);
-    else fp8_to_wide_kernel<OUT, SCALED, 256, 4><<<c.grid, 256, 0, st>>>(in, out, n, scale);
-    return after_launch();
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    if (c.big) return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 8>, dim3(c.grid), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
+    return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 4>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
 }
 
 extern "C" int fp8b_dequant_f16(const uint8_t* in, void* out, size_t n, const float* scale, void* stream)
@@ -512,9 +561,9 @@ static int launch_encode_vec(const void* in, uint8_t* out, size_t n, const float
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const CastShape c = cast_shape(n / EPV);
-    if (c.big) wide_to_fp8_kernel<IN, PRESCALE, 1024, 4><<<c.grid, 1024, 0, st>>>(in, out, n, prescale);
-    else wide_to_fp8_kernel<IN, PRESCALE, 256, 4><<<c.grid, 256, 0, st>>>(in, out, n, prescale);
-    return after_launch();
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    if (c.big) return launch_ex(wide_to_fp8_kernel<IN, PRESCALE, 1024, 4>, dim3(c.grid), dim3(1024), 0, st, 1, 1, pdl, in, out, n, prescale);
+    return launch_ex(wide_to_fp8_kernel<IN, PRESCALE, 256, 4>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, prescale);
 }
 
 template <int IN>
@@ -546,7 +595,11 @@ template <int IN>
 static int launch_amax(const void* in, size_t n, uint32_t* scratch, cudaStream_t st)
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
-    if (aligned(in, 16)) amax_kernel<IN><<<cast_grid(n / EPV + 1), kCastThreads, 0, st>>>(in, n, scratch);
+    if (aligned(in, 16)) {
+        const size_t cap = (size_t)device_info().sm_count * tune_int("FP8B_AMAX_CAP", 8);
+        const size_t want = (n / EPV + kCastThreads * 4 - 1) / (kCastThreads * 4) + 1;
+        amax_kernel<IN><<<(int)(want < cap ? want : cap), kCastThreads, 0, st>>>(in, n, scratch);
+    }
     else amax_scalar_kernel<IN><<<cast_grid(n), kCastThreads, 0, st>>>(in, n, scratch);
     return after_launch();
 }
@@ -605,17 +658,17 @@ int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, LaunchFn 
 template <int IN>
 int launch_encode_batch(const CastBatch& b, int grid, int big, cudaStream_t st)
 {
-    if (big) wide_to_fp8_batch_kernel<IN, 1024, 4><<<grid, 1024, 0, st>>>(b);
-    else wide_to_fp8_batch_kernel<IN, 256, 4><<<grid, 256, 0, st>>>(b);
-    return after_launch();
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    if (big) return launch_ex(wide_to_fp8_batch_kernel<IN, 1024, 4>, dim3(grid), dim3(1024), 0, st, 1, 1, pdl, b);
+    return launch_ex(wide_to_fp8_batch_kernel<IN, 256, 4>, dim3(grid), dim3(256), 0, st, 1, 1, pdl, b);
 }
 
 template <int OUT>
 int launch_decode_batch(const CastBatch& b, int grid, int big, cudaStream_t st)
 {
-    if (big) fp8_to_wide_batch_kernel<OUT, 512, 8><<<grid, 512, 0, st>>>(b);
-    else fp8_to_wide_batch_kernel<OUT, 256, 4><<<grid, 256, 0, st>>>(b);
-    return after_launch();
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    if (big) return launch_ex(fp8_to_wide_batch_kernel<OUT, 512, 8>, dim3(grid), dim3(512), 0, st, 1, 1, pdl, b);
+    return launch_ex(fp8_to_wide_batch_kernel<OUT, 256, 4>, dim3(grid), dim3(256), 0, st, 1, 1, pdl, b);
 }
 
 }  // namespace

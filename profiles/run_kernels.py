@@ -41,7 +41,7 @@ def main():
                                   None, 0, None, None, 0, algo, st)
             assert rc == 0, rc
     elif which in ("quant", "dequant"):
-        n = 21504 * 3072 * 8
+        n = 21504 * 3072 * (8 if os.environ.get("FP8B_PROFILE_BIG") else 1)      # the largest FLUX tensor of C5 (198 MB of traffic)
         x = (torch.randn(n, generator=g, device=dev) * 0.02).to(torch.bfloat16)
         q = torch.empty(n, dtype=torch.uint8, device=dev)
         h = torch.empty(n, dtype=torch.float16, device=dev)

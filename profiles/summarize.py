@@ -118,8 +118,8 @@ def main():
             for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 w.writerow([k, v[0], round(v[1] / 1e3, 2), round(100 * v[1] / tot, 2), round(v[1] / v[0] / 1e3, 3)])
         md.append(f"\n## launch list of `bench.py --steps 2 --warmup 3 --no-cpu` ({rnd}_launches.csv)\n")
-        md.append("Includes the data-generation kernels of the benchmark set-up (torch randn / copy); the timed regions "
-                  "contain only `fp8b::` kernels.\n")
+        md.append("Captured with `-k regex:fp8` (this library's kernels only; the benchmark's torch data-generation kernels "
+                  "are filtered out).  Cold-cache and serialised: compare shares, not absolutes.\n")
         md.append("| kernel | launches | total µs | share | avg µs |\n|---|---|---|---|---|")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
             md.append(f"| `{k[:80]}` | {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0] / 1e3:.2f} |")

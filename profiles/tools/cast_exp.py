@@ -50,3 +50,11 @@ for shape in (1, 2):
     e = 3.0 * total / timeit(lambda: L.fp8b_encode_batch(es, cnt, 2, sp())) / 1e6
     d = 3.0 * total / timeit(lambda: L.fp8b_dequant_batch(ds, cnt, 1, sp())) / 1e6
     print(f"FP8B_CAST_SHAPE={shape}: encode {e:7.0f}  dequant {d:7.0f} GB/s", flush=True)
+
+# amax (read-only pass of fp8_quantize): 2 B/element
+scales = torch.empty(2, device=dev); scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+for lib, tag in ((L, "current"),):
+    for cap in (2, 3, 4, 6, 8):
+        os.environ["FP8B_AMAX_CAP"] = str(cap)
+        ms = timeit(lambda: lib.fp8b_amax_scale(P(src.data_ptr()), 2, total, P(scales.data_ptr()), P(scales.data_ptr() + 4), P(scratch.data_ptr()), sp()))
+        print(f"amax bf16 {tag} cap {cap}/SM: {2.0 * total / ms / 1e6:7.0f} GB/s", flush=True)

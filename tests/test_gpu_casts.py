@@ -300,3 +300,28 @@ def test_batch_casts_validation():
     assert L.fp8b_encode_batch(make_spans([(None, q.data_ptr(), 16)]), 1, BF16, stream_ptr()) == -1
     assert L.fp8b_dequant_batch(make_spans([(q.data_ptr(), None, 4)]), 1, F16, stream_ptr()) == -1
     assert L.fp8b_dequant_batch(make_spans([(None, None, 0)]), 1, F16, stream_ptr()) == 0
+
+
+def test_casts_under_pdl_see_fresh_data():
+    """The tile kernels are launched with programmatic dependent launch (resident before their predecessor has
+    finished).  Inputs produced by the kernel just before -- a torch op, or another cast -- must still be seen:
+    regenerate x on the device right before every call and chain encode -> dequant without a sync."""
+    import fp8_mps_native
+    g = torch.Generator(device=DEV).manual_seed(11)
+    n = (1 << 22) + 24
+    for it in range(25):
+        x = (torch.randn(n, device=DEV, generator=g) * (0.5 + it)).to(torch.bfloat16)
+        q = fp8_mps_native.fp8_encode(x)                       # predecessor: the torch cast kernel that wrote x
+        h = fp8_mps_native.fp8_dequantize_to(q, torch.float16)  # predecessor: our own encode kernel
+        qq, inv = fp8_mps_native.fp8_quantize(x)               # amax -> finalize -> encode(prescale) chain
+        torch.cuda.synchronize()
+        q_ref = fp8_mps_native.fp8_encode(x)
+        torch.cuda.synchronize()
+        h_ref = fp8_mps_native.fp8_dequantize_to(q_ref, torch.float16)
+        torch.cuda.synchronize()
+        qq_ref, inv_ref = fp8_mps_native.fp8_quantize(x)
+        torch.cuda.synchronize()
+        assert torch.equal(q, q_ref) and torch.equal(h, h_ref), f"iteration {it}"
+        assert torch.equal(qq, qq_ref) and torch.equal(inv, inv_ref), f"iteration {it} (quantize)"
+    xs = x[:70001].float().cpu()
+    assert np.array_equal(q[:70001].cpu().numpy(), c_oracle.encode(xs.numpy()))
