@@ -462,7 +462,11 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
         out[name] = {"ms_per_sweep": round(ms_sweep, 3), "value": round(gbs, 1), "unit": "GB/s", "elements": total,
                      "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
                                   "frac": round(gbs / peaks["hbm"], 4), "frac_of_nominal_8000": round(gbs / 8000.0, 4),
-                                  "traffic": None, "peak_source": peaks["source"]},
+                                  "traffic": profile_traffic("quant" if name.startswith("quantize") else "dequant"),
+                                  "traffic_note": "ncu capture of ONE launch on the largest tensor of the set (21504x3072, "
+                                                  "198 180 864 algorithmic bytes); below that because part of the output "
+                                                  "is still dirty in L2 when the 3-launch capture ends",
+                                  "peak_source": peaks["source"]},
                      "launches_per_sweep": launches, "l2": "35.5 GB working set per sweep >> L2",
                      "four_streams": {"ms_per_sweep": round(res[4][0], 3), "value": round(res[4][1], 1), "unit": "GB/s",
                                       "frac": round(res[4][1] / peaks["hbm"], 4),
