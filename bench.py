@@ -290,7 +290,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -492,6 +492,15 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
 
 # --------------------------------------------------------------------------- main
 
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -501,6 +510,12 @@ def main():
     ap.add_argument("--no-sub", action="store_true", help="headline only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly ONE line: the JSON.  Libraries chat on fd 1 (NCCL prints its version there, the
+    # patch prints like the reference), so fd 1 is pointed at stderr for the run and the line goes to the saved fd.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -759,7 +774,7 @@ def main():
     if dist is not None:
         dist.barrier()
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
