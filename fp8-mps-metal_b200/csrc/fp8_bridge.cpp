@@ -57,7 +57,7 @@ torch::Tensor as_device_f32(const torch::Tensor& t, const torch::Device& dev)
 torch::Tensor fp8_scaled_mm_fused(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
                                   c10::optional<torch::Tensor> bias, c10::optional<torch::Tensor> scale_result,
                                   c10::optional<at::ScalarType> out_dtype, int64_t algo,
-                                  c10::optional<torch::Tensor> out)
+                                  c10::optional<torch::Tensor> out, int64_t a_format, int64_t b_format)
 {
     TORCH_CHECK(A.dtype() == torch::kUInt8, "A must be uint8 (FP8 encoded)");
     TORCH_CHECK(B.dtype() == torch::kUInt8, "B must be uint8 (FP8 encoded)");
@@ -109,9 +109,15 @@ torch::Tensor fp8_scaled_mm_fused(torch::Tensor A, torch::Tensor B, torch::Tenso
     }
 
     if (M == 0 || N == 0) return C;
-    int rc = fp8b_scaled_mm(u8_ptr(A), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt), (int)M, (int)N, (int)K, ldc,
-                            sa.data_ptr<float>(), (int)sa.numel(), sb.data_ptr<float>(), (int)sb.numel(),
-                            bias_ptr, bias_dt, sr_ptr, nullptr, 0, (int)algo, current_stream());
+    int rc;
+    if (a_format != FP8B_E4M3FN || b_format != FP8B_E4M3FN)
+        rc = fp8b_scaled_mm_fmt(u8_ptr(A), (int)a_format, u8_ptr(B), (int)b_format, C.data_ptr(), to_fp8b_dtype(odt),
+                                (int)M, (int)N, (int)K, ldc, sa.data_ptr<float>(), (int)sa.numel(), sb.data_ptr<float>(),
+                                (int)sb.numel(), bias_ptr, bias_dt, sr_ptr, (int)algo, current_stream());
+    else
+        rc = fp8b_scaled_mm(u8_ptr(A), u8_ptr(B), C.data_ptr(), to_fp8b_dtype(odt), (int)M, (int)N, (int)K, ldc,
+                                sa.data_ptr<float>(), (int)sa.numel(), sb.data_ptr<float>(), (int)sb.numel(),
+                                bias_ptr, bias_dt, sr_ptr, nullptr, 0, (int)algo, current_stream());
     check_status(rc, "fp8b_scaled_mm");
     return C;
 }
@@ -119,7 +125,8 @@ torch::Tensor fp8_scaled_mm_fused(torch::Tensor A, torch::Tensor B, torch::Tenso
 // ---- the reference bridge's three ops (fp8_bridge.cpp:165, :265, :312) ------------------------
 torch::Tensor fp8_scaled_mm(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b)
 {
-    return fp8_scaled_mm_fused(A, B, scale_a, scale_b, c10::nullopt, c10::nullopt, c10::nullopt, FP8B_MM_AUTO, c10::nullopt);
+    return fp8_scaled_mm_fused(A, B, scale_a, scale_b, c10::nullopt, c10::nullopt, c10::nullopt, FP8B_MM_AUTO, c10::nullopt,
+                               FP8B_E4M3FN, FP8B_E4M3FN);
 }
 
 torch::Tensor fp8_dequantize(torch::Tensor input, torch::Tensor scale)
@@ -137,15 +144,16 @@ torch::Tensor fp8_dequantize(torch::Tensor input, torch::Tensor scale)
 }
 
 // FP8 -> dtype exact cast (no scale): the `.to(dtype)` route of the patch in one pass.
-torch::Tensor fp8_dequantize_to(torch::Tensor input, at::ScalarType dtype)
+torch::Tensor fp8_dequantize_to(torch::Tensor input, at::ScalarType dtype, int64_t format)
 {
     TORCH_CHECK(input.dtype() == torch::kUInt8, "input must be uint8");
     TORCH_CHECK(input.is_cuda(), "input must be a CUDA tensor");
     c10::cuda::CUDAGuard guard(input.device());
     torch::Tensor in = input.contiguous();
     torch::Tensor out = torch::empty(in.sizes(), torch::TensorOptions().dtype(dtype).device(in.device()));
-    check_status(fp8b_dequant(u8_ptr(in), out.data_ptr(), to_fp8b_dtype(dtype), (size_t)in.numel(), current_stream()),
-                 "fp8b_dequant");
+    check_status(fp8b_dequant_fmt(u8_ptr(in), (int)format, out.data_ptr(), to_fp8b_dtype(dtype), (size_t)in.numel(), nullptr,
+                                  current_stream()),
+                 "fp8b_dequant_fmt");
     return out;
 }
 
@@ -356,13 +364,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("fp8_encode_many", &fp8_encode_many, "Float to FP8 encoding of a list of tensors in one launch", py::arg("inputs"));
     m.def("fp8_dequantize_many", &fp8_dequantize_many, "FP8 to float cast of a list of tensors in one launch",
           py::arg("inputs"), py::arg("dtype"));
-    m.def("fp8_dequantize_to", &fp8_dequantize_to, "FP8 to float32/float16/bfloat16 exact cast",
-          py::arg("input"), py::arg("dtype"));
+    m.def("fp8_dequantize_to", &fp8_dequantize_to, "FP8 (e4m3fn or e5m2) to float32/float16/bfloat16 exact cast",
+          py::arg("input"), py::arg("dtype"), py::arg("format") = 0);
     m.def("fp8_scaled_mm_fused", &fp8_scaled_mm_fused,
           "FP8 scaled matmul with fused scales, bias, scale_result and output cast",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias") = py::none(),
           py::arg("scale_result") = py::none(), py::arg("out_dtype") = py::none(), py::arg("algo") = 0,
-          py::arg("out") = py::none());
+          py::arg("out") = py::none(), py::arg("a_format") = 0, py::arg("b_format") = 0);
     m.def("fp8_scaled_mm_multicast", &fp8_scaled_mm_multicast,
           "FP8 scaled matmul storing through an NVSwitch multicast address (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out_dtype"),
@@ -374,6 +382,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.attr("OPT_PDL") = (int)FP8B_OPT_PDL;
     m.attr("OPT_STATIC_WEIGHTS") = (int)FP8B_OPT_STATIC_WEIGHTS;
     m.def("version", []() { return fp8b_version(); });
+    m.attr("FMT_E4M3FN") = (int)FP8B_E4M3FN;
+    m.attr("FMT_E5M2") = (int)FP8B_E5M2;
     m.attr("ALGO_AUTO") = (int)FP8B_MM_AUTO;
     m.attr("ALGO_GEMV") = (int)FP8B_MM_GEMV;
     m.attr("ALGO_TCGEN05") = (int)FP8B_MM_TCGEN05;

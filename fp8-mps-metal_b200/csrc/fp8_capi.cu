@@ -110,6 +110,21 @@ extern "C" int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const v
     return select_algo(a);
 }
 
+static int scaled_mm_impl(MMArgs& a, int algo)
+{
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (a.M == 0 || a.N == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (algo == FP8B_MM_AUTO) algo = select_algo(a);
+    switch (algo) {
+        case FP8B_MM_GEMV: return launch_gemv(a);
+        case FP8B_MM_TCGEN05: return launch_gemm_tcgen05(a);
+        case FP8B_MM_SIMT: return launch_gemm_simt(a);
+        default: return FP8B_ERR_INVALID;
+    }
+}
+
 extern "C" int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out_dtype,
                               int M, int N, int K, int64_t ldc,
                               const float* scale_a, int scale_a_len,
@@ -125,17 +140,27 @@ extern "C" int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int o
     a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
     a.ws = workspace; a.ws_bytes = workspace_bytes; a.st = (cudaStream_t)stream;
     a.store_mc = 0;
-    int rc = validate(a);
-    if (rc != FP8B_OK) return rc;
-    if (M == 0 || N == 0) return FP8B_OK;
-    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
-    if (algo == FP8B_MM_AUTO) algo = select_algo(a);
-    switch (algo) {
-        case FP8B_MM_GEMV: return launch_gemv(a);
-        case FP8B_MM_TCGEN05: return launch_gemm_tcgen05(a);
-        case FP8B_MM_SIMT: return launch_gemm_simt(a);
-        default: return FP8B_ERR_INVALID;
-    }
+    return scaled_mm_impl(a, algo);
+}
+
+extern "C" int fp8b_scaled_mm_fmt(const uint8_t* A, int a_format, const uint8_t* B, int b_format, void* C, int out_dtype,
+                                  int M, int N, int K, int64_t ldc,
+                                  const float* scale_a, int scale_a_len,
+                                  const float* scale_b, int scale_b_len,
+                                  const void* bias, int bias_dtype,
+                                  const float* scale_result,
+                                  int algo, void* stream)
+{
+    if ((a_format != FP8B_E4M3FN && a_format != FP8B_E5M2) || (b_format != FP8B_E4M3FN && b_format != FP8B_E5M2))
+        return FP8B_ERR_INVALID;
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = nullptr; a.ws_bytes = 0; a.st = (cudaStream_t)stream;
+    a.store_mc = 0;
+    a.a_fmt = a_format; a.b_fmt = b_format;
+    return scaled_mm_impl(a, algo);
 }
 
 extern "C" int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void* C_multicast, int out_dtype,

@@ -85,7 +85,7 @@ struct TileWalk {
 };
 
 // FP8 -> wide.  OUT: FP8B_F16 / FP8B_BF16 / FP8B_F32.  SCALED (f16 only): fp16 multiply by RN16(scale).
-template <int OUT, bool SCALED, int THREADS, int UNROLL>
+template <int OUT, bool SCALED, int THREADS, int UNROLL, int FMT = 0>
 __device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t vbegin,
                                             size_t nvec, uint32_t s2)
 {
@@ -104,13 +104,13 @@ __device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint
             uint4 o;
             if (OUT == FP8B_F32) {
                 uint32_t lo, hi;
-                dec4_f16x2(w[u].x, lo, hi);
+                dec4_fmt_f16x2<FMT>(w[u].x, lo, hi);
                 const float2 a = __half22float2(*reinterpret_cast<__half2*>(&lo));
                 const float2 c = __half22float2(*reinterpret_cast<__half2*>(&hi));
                 o = make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y));
             } else {
-                dec4_f16x2(w[u].x, o.x, o.y);
-                dec4_f16x2(w[u].y, o.z, o.w);
+                dec4_fmt_f16x2<FMT>(w[u].x, o.x, o.y);
+                dec4_fmt_f16x2<FMT>(w[u].y, o.z, o.w);
                 if (SCALED) {                                   // fp16 multiply, native.py:122
                     const __half2 sc = *reinterpret_cast<const __half2*>(&s2);
                     uint32_t* q = &o.x;
@@ -131,11 +131,11 @@ __device__ __forceinline__ void decode_tile(const uint8_t* __restrict__ in, uint
 }
 
 // ragged tail (< one vector) of a tensor, one thread
-template <int OUT, bool SCALED>
+template <int OUT, bool SCALED, int FMT = 0>
 __device__ __forceinline__ void decode_tail(const uint8_t* in, void* out, size_t from, size_t n, const float* scale)
 {
     for (size_t i = from; i < n; ++i) {
-        const float f = dec1_f32(in[i]);
+        const float f = dec1_fmt_f32(in[i], FMT);
         if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
         else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
         else {
@@ -146,7 +146,7 @@ __device__ __forceinline__ void decode_tail(const uint8_t* in, void* out, size_t
     }
 }
 
-template <int OUT, bool SCALED, int THREADS, int UNROLL>
+template <int OUT, bool SCALED, int THREADS, int UNROLL, int FMT = 0>
 __global__ void __launch_bounds__(THREADS)
 fp8_to_wide_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
                    const float* __restrict__ scale)
@@ -163,19 +163,19 @@ fp8_to_wide_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_
     uint8_t* o8 = reinterpret_cast<uint8_t*>(out);
     TileWalk<THREADS * UNROLL> walk(nvec);
     for (size_t r = 0; r < walk.rounds; ++r)
-        decode_tile<OUT, SCALED, THREADS, UNROLL>(in, o8, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s2);
-    if (walk.rem_begin < walk.rem_end) decode_tile<OUT, SCALED, THREADS, UNROLL>(in, o8, walk.rem_begin, walk.rem_end, s2);
-    if (blockIdx.x == 0 && threadIdx.x == 0) decode_tail<OUT, SCALED>(in, out, nvec * EPV, n, scale);
+        decode_tile<OUT, SCALED, THREADS, UNROLL, FMT>(in, o8, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s2);
+    if (walk.rem_begin < walk.rem_end) decode_tile<OUT, SCALED, THREADS, UNROLL, FMT>(in, o8, walk.rem_begin, walk.rem_end, s2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) decode_tail<OUT, SCALED, FMT>(in, out, nvec * EPV, n, scale);
 }
 
-template <int OUT, bool SCALED>
+template <int OUT, bool SCALED, int FMT = 0>
 __global__ void __launch_bounds__(kCastThreads)
 fp8_to_wide_scalar_kernel(const uint8_t* __restrict__ in, void* __restrict__ out, size_t n,
                           const float* __restrict__ scale)
 {
     const size_t stride = (size_t)gridDim.x * kCastThreads;
     for (size_t i = (size_t)blockIdx.x * kCastThreads + threadIdx.x; i < n; i += stride) {
-        float f = dec1_f32(in[i]);
+        float f = dec1_fmt_f32(in[i], FMT);
         if (OUT == FP8B_F32) reinterpret_cast<float*>(out)[i] = f;
         else if (OUT == FP8B_BF16) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(f);
         else {
@@ -512,14 +512,14 @@ static int cast_grid(size_t work_items) {
 using namespace fp8b;
 
 // fp8 -> wide launch: big tiles = 512 threads x 8, small = 256 x 4
-template <int OUT, bool SCALED>
+template <int OUT, bool SCALED, int FMT = 0>
 static int launch_decode_vec(const uint8_t* in, void* out, size_t n, const float* scale, cudaStream_t st)
 {
     constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
     const CastShape c = cast_shape(n / EPV);
     const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
-    if (c.big) return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 8>, dim3(c.grid), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
-    return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 4>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
+    if (c.big) return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 8, FMT>, dim3(c.grid), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
+    return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 4, FMT>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
 }
 
 extern "C" int fp8b_dequant_f16(const uint8_t* in, void* out, size_t n, const float* scale, void* stream)
@@ -553,6 +553,33 @@ extern "C" int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t 
         fp8_to_wide_scalar_kernel<FP8B_F32, false><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, nullptr);
     }
     return after_launch();
+}
+
+// float8_e5m2 -> wide (decode only; see fp8_codec.cuh).  scale: optional, fp16 output only, applied like fp8b_dequant_f16.
+template <int OUT, bool SCALED>
+static int launch_decode_e5m2(const uint8_t* in, void* out, size_t n, const float* scale, cudaStream_t st)
+{
+    constexpr int EPV = (OUT == FP8B_F32) ? 4 : 8;
+    if (aligned(in, EPV) && aligned(out, 16)) return launch_decode_vec<OUT, SCALED, 1>(in, out, n, scale, st);
+    fp8_to_wide_scalar_kernel<OUT, SCALED, 1><<<cast_grid(n), kCastThreads, 0, st>>>(in, out, n, scale);
+    return after_launch();
+}
+
+extern "C" int fp8b_dequant_fmt(const uint8_t* in, int in_format, void* out, int out_dtype, size_t n, const float* scale,
+                                void* stream)
+{
+    if (!valid_dtype(out_dtype) || (in_format != FP8B_E4M3FN && in_format != FP8B_E5M2)) return FP8B_ERR_INVALID;
+    if (scale && out_dtype != FP8B_F16) return FP8B_ERR_INVALID;
+    if (in_format == FP8B_E4M3FN)
+        return out_dtype == FP8B_F16 ? fp8b_dequant_f16(in, out, n, scale, stream) : fp8b_dequant(in, out, out_dtype, n, stream);
+    if (n == 0) return FP8B_OK;
+    if (!in || !out) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == FP8B_F32) return launch_decode_e5m2<FP8B_F32, false>(in, out, n, nullptr, st);
+    if (out_dtype == FP8B_BF16) return launch_decode_e5m2<FP8B_BF16, false>(in, out, n, nullptr, st);
+    return scale ? launch_decode_e5m2<FP8B_F16, true>(in, out, n, scale, st)
+                 : launch_decode_e5m2<FP8B_F16, false>(in, out, n, nullptr, st);
 }
 
 // wide -> fp8 launch: big tiles = 1024 threads x 4, small = 256 x 4

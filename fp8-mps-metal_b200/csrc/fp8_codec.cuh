@@ -58,6 +58,30 @@ __device__ __forceinline__ float dec1_f32(uint8_t b) {
     return __half2float(__ushort_as_half((unsigned short)(v & 0xFFFF)));
 }
 
+// ---------------------------------------------------------------- float8_e5m2 (decode only)
+// e5m2 is the upper byte of an IEEE binary16: decode = byte << 8, exact, +-inf and NaN preserved (the format's own
+// definition, pinned to PyTorch's CPU cast in tests/golden/e5m2_golden.npz).  The reference accepts e5m2 tensors
+// but decodes them as e4m3fn (fp8_mps_patch.py:48-49,65) -- there is no reference codec to follow.
+// Formats are numbered as in include/fp8_b200.h: 0 = e4m3fn, 1 = e5m2.
+
+// 4 e5m2 bytes -> two f16x2 registers: two byte permutes, no conversion instruction.
+__device__ __forceinline__ void dec4_e5m2_f16x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    lo = __byte_perm(w, 0u, 0x1404);        // bytes {0, b0, 0, b1}
+    hi = __byte_perm(w, 0u, 0x3424);        // bytes {0, b2, 0, b3}
+}
+
+__device__ __forceinline__ float dec1_e5m2_f32(uint8_t b) {
+    return __half2float(__ushort_as_half((unsigned short)((unsigned)b << 8)));
+}
+
+// 4 bytes of format FMT -> two f16x2 registers, reference NaN rule for e4m3fn (NaN -> 0), IEEE for e5m2.
+template <int FMT>
+__device__ __forceinline__ void dec4_fmt_f16x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    if (FMT == 0) dec4_f16x2(w, lo, hi); else dec4_e5m2_f16x2(w, lo, hi);
+}
+
+__device__ __forceinline__ float dec1_fmt_f32(uint8_t b, int fmt) { return fmt ? dec1_e5m2_f32(b) : dec1_f32(b); }
+
 // ---------------------------------------------------------------- encode
 
 // fp32 input repair, steps (1)-(3) above.

@@ -3,7 +3,7 @@
 // This is the device path for problems the TMA/tcgen05 kernel cannot take (K % 16 != 0,
 // unaligned base pointers) -- the library has no CPU fallback, so something on the GPU must serve
 // them -- and an independent on-device cross-check of the tcgen05 kernel in the tests.
-// Same arithmetic as fp8_scaled_matmul_kernel (fp8_matmul.metal:99-147): masked decode (NaN -> 0),
+// Same arithmetic as fp8_scaled_matmul_kernel (fp8_matmul.metal:99-147): masked decode (NaN -> 0; e5m2 operands IEEE),
 // fp32 FMA accumulation, fused epilogue.  64x64 output tile per CTA, 4x4 outputs per thread,
 // 32-wide K panels staged in shared memory as fp32.
 #include "fp8_mm.cuh"
@@ -15,7 +15,8 @@ constexpr int kSimtK = 32;
 constexpr int kSimtThreads = 256;
 
 __global__ void __launch_bounds__(kSimtThreads)
-fp8_gemm_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi)
+fp8_gemm_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi,
+                     int a_fmt, int b_fmt)
 {
     __shared__ float As[kSimtK][kSimtTile + 4];
     __shared__ float Bs[kSimtK][kSimtTile + 4];
@@ -34,8 +35,8 @@ fp8_gemm_simt_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int k = k0 + lk + j;
-            As[lk + j][lrow] = (am < M && k < K) ? dec1_f32(A[(size_t)am * K + k]) : 0.0f;
-            Bs[lk + j][lrow] = (bn < N && k < K) ? dec1_f32(B[(size_t)bn * K + k]) : 0.0f;
+            As[lk + j][lrow] = (am < M && k < K) ? dec1_fmt_f32(A[(size_t)am * K + k], a_fmt) : 0.0f;
+            Bs[lk + j][lrow] = (bn < N && k < K) ? dec1_fmt_f32(B[(size_t)bn * K + k], b_fmt) : 0.0f;
         }
         __syncthreads();
 #pragma unroll
@@ -68,7 +69,7 @@ int launch_gemm_simt(const MMArgs& a)
     const Epi epi = make_epi(a);
     dim3 grid((a.N + kSimtTile - 1) / kSimtTile, (a.M + kSimtTile - 1) / kSimtTile, 1);
     if (grid.y > 65535) return FP8B_ERR_UNSUPPORTED;
-    fp8_gemm_simt_kernel<<<grid, kSimtThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi);
+    fp8_gemm_simt_kernel<<<grid, kSimtThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi, a.a_fmt, a.b_fmt);
     return after_launch();
 }
 

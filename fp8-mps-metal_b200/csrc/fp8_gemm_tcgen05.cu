@@ -74,7 +74,9 @@ struct GemmParams {
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
     int store_mc;                            // C is an NVSwitch multicast address: store with multimem.st
     long long* dbg;                          // FP8B_GEMM_DEBUG & 16: per-tile clock64 stamps of CTA 0 (profiling only)
-    int debug;                               // FP8B_GEMM_DEBUG profiling knob: 1 = no stores, 2 = drain TMEM only
+    int debug;                               // bits 0-7: FP8B_GEMM_DEBUG profiling knob (1 = no stores, 2 = drain TMEM only);
+                                             // bit 8 / bit 9: A / B operand is e5m2 (kept in this word so that the
+                                             // parameter block -- and with it the tuned schedule -- does not change)
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -225,8 +227,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor for kind::f8f6f4: D = f32 (bits 4-5 = 1), A = B = e4m3 (formats 0),
-// both K-major (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
+// Instruction descriptor for kind::f8f6f4: D = f32 (bits 4-5 = 1), A format at [7,10), B format at [10,13)
+// (0 = e4m3, 1 = e5m2; OR-ed in at run time from GemmParams::debug bits 8/9), both K-major (bits 15,16 = 0),
+// N >> 3 at [17,23), M >> 4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -366,6 +369,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // tensor pipe may have to absorb (measured: a 90-instruction body cost 15 % of MMA throughput).
         if (is_leader) {
             constexpr uint32_t idesc = make_idesc(kTileM, BN);
+            const uint32_t idesc_fmt = (((uint32_t)p.debug >> 8) & 1u) << 7 | (((uint32_t)p.debug >> 9) & 1u) << 10;
             const bool elected = elect_one();
             const uint64_t desc_a0 = make_smem_desc(smem_base);
             const uint64_t desc_b0 = make_smem_desc(smem_base + Cfg::kABytes);
@@ -378,7 +382,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tc_fence_after();
                 const long long t_m1 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                const uint32_t idesc_t = (tile < p.full_tiles) ? idesc : make_idesc(kTileM, BN / 2);
+                const uint32_t idesc_t = ((tile < p.full_tiles) ? idesc : make_idesc(kTileM, BN / 2)) | idesc_fmt;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
                     tc_fence_after();
@@ -496,7 +500,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     for (int j = 0; j < 32; ++j) {
                         const float a = __uint_as_float(r[j]);
                         if (a != a && m_ok && n0 + j < p.N)
-                            r[j] = __float_as_uint(slow_dot_masked(p.A + (size_t)m * p.K, p.B + (size_t)(n0 + j) * p.K, p.K));
+                            r[j] = __float_as_uint(slow_dot_fmt(p.A + (size_t)m * p.K, p.B + (size_t)(n0 + j) * p.K, p.K,
+                                                                (p.debug >> 8) & 1, (p.debug >> 9) & 1));
                     }
                 }
                 if (full_chunk && p.vec_store_ok) {
@@ -673,7 +678,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     const size_t esz = dtype_size(a.out_dtype);
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
     p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
-    p.debug = tune_int("FP8B_GEMM_DEBUG", 0);
+    p.debug = (tune_int("FP8B_GEMM_DEBUG", 0) & 0xFF) | (a.a_fmt ? 0x100 : 0) | (a.b_fmt ? 0x200 : 0);
     p.store_mc = a.store_mc;
     p.dbg = nullptr;
     if (p.debug & 16) {                      // profiling only: allocates and synchronises

@@ -448,7 +448,8 @@ fp8_gemv_xq_kernel(const GemvXqParams xp)
 
 // Any K / any alignment: byte loads, masked scalar decode, fp32 FMA.  Correct, not fast.
 __global__ void __launch_bounds__(kGemvThreads)
-fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi)
+fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict__ B, int M, int N, int K, const Epi epi,
+                        int a_fmt, int b_fmt)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kGemvWarps + warp;
@@ -457,7 +458,7 @@ fp8_gemv_generic_kernel(const uint8_t* __restrict__ A, const uint8_t* __restrict
     for (int m = 0; m < M; ++m) {
         const uint8_t* x = A + (size_t)m * K;
         float acc = 0.0f;
-        for (int k = lane; k < K; k += 32) acc = __fmaf_rn(dec1_f32(x[k]), dec1_f32(wrow[k]), acc);
+        for (int k = lane; k < K; k += 32) acc = __fmaf_rn(dec1_fmt_f32(x[k], a_fmt), dec1_fmt_f32(wrow[k], b_fmt), acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
         if (lane == 0) epi_store(epi, m, row, epi_apply(epi, acc, m, row));
@@ -495,12 +496,18 @@ int launch_gemv(const MMArgs& a)
     // M >= 2 -> warp-level tensor-core kernel (weights streamed once for all M rows).
     // FP8B_GEMV_IMPL=1 / 2 forces the first / second (profiling knob).
     const int impl = tune_int("FP8B_GEMV_IMPL", 0);
+    if (a.a_fmt | a.b_fmt) {        // an e5m2 operand: the warp-MMA kernel has all four type pairs; else the generic kernel
+        if (gemv_mma_supported(a)) return launch_gemv_mma(a);
+        fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, make_epi(a),
+                                                                                             a.a_fmt, a.b_fmt);
+        return after_launch();
+    }
     if (gemv_mma_supported(a) && (impl == 2 || (impl == 0 && a.M >= 2))) return launch_gemv_mma(a);
     if (gemv_rows_supported(a) && (impl == 3)) return launch_gemv_rows(a);
     const Epi epi = make_epi(a);
     const bool fast = (a.K % 16 == 0) && a.K >= 16 && aligned(a.A, 16) && aligned(a.B, 16);
     if (!fast) {
-        fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi);
+        fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, epi, 0, 0);
         return after_launch();
     }
     return launch_gemv_fhfma(a, epi, nullptr, 0, nullptr);

@@ -49,14 +49,22 @@ __device__ __forceinline__ uint4 ldg_cached16(const uint8_t* p) {
     return r;
 }
 
-__device__ __forceinline__ void mma_e4m3_m16n8k32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                  uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k32.row.col.f32.e4m3.e4m3.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+// WF / XF: format of the 16-row operand (weights) and of the 8-column operand (activations); 0 = e4m3fn, 1 = e5m2.
+template <int WF, int XF>
+__device__ __forceinline__ void mma_f8_m16n8k32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t b0, uint32_t b1) {
+#define FP8B_MMA(TA, TB) \
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.f32." TA "." TB ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) \
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1))
+    if (WF == 0 && XF == 0) FP8B_MMA("e4m3", "e4m3");
+    else if (WF == 0 && XF == 1) FP8B_MMA("e4m3", "e5m2");
+    else if (WF == 1 && XF == 0) FP8B_MMA("e5m2", "e4m3");
+    else FP8B_MMA("e5m2", "e5m2");
+#undef FP8B_MMA
 }
 
-template <int NB, int BATCH>            // NB = 1: M <= 8, NB = 2: M <= 16; BATCH 64-byte k-steps per load group
+template <int NB, int BATCH, int WF = 0, int XF = 0>   // NB = 1: M <= 8, NB = 2: M <= 16; BATCH 64-byte k-steps per load group
 __global__ void __launch_bounds__(kMmaThreads)
 fp8_gemv_mma_kernel(const GemvMmaParams p)
 {
@@ -119,11 +127,11 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
         load_x(nxa, nxb, kb + 64 * BATCH);
 #pragma unroll
         for (int s = 0; s < BATCH; ++s) {
-            mma_e4m3_m16n8k32(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
-            mma_e4m3_m16n8k32(c[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
+            mma_f8_m16n8k32<WF, XF>(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
+            mma_f8_m16n8k32<WF, XF>(c[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
             if (NB == 2) {
-                mma_e4m3_m16n8k32(c[1], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xb[s].x, xb[s].y);
-                mma_e4m3_m16n8k32(c[1], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xb[s].z, xb[s].w);
+                mma_f8_m16n8k32<WF, XF>(c[1], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xb[s].x, xb[s].y);
+                mma_f8_m16n8k32<WF, XF>(c[1], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xb[s].z, xb[s].w);
             }
         }
 #pragma unroll
@@ -150,7 +158,8 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < kMmaWarps; ++w) v += part[w][row][m];
-        if (v != v) v = slow_dot_masked(p.A + (size_t)m * K, p.B + (size_t)n * K, K);
+        if (v != v) v = (WF | XF) ? slow_dot_fmt(p.A + (size_t)m * K, p.B + (size_t)n * K, K, XF, WF)
+                              : slow_dot_masked(p.A + (size_t)m * K, p.B + (size_t)n * K, K);
         epi_store(p.epi, m, n, epi_apply(p.epi, v, m, n));
     }
 }
@@ -171,6 +180,17 @@ int launch_gemv_mma(const MMArgs& a)
     const bool pdl = p.static_b != 0;      // without static weights PDL only hides launch latency, which graphs already do
     const int grid = (a.N + kMmaRows - 1) / kMmaRows;
     const int batch = tune_int("FP8B_GEMV_BATCH", 4);
+    if (a.a_fmt | a.b_fmt) {                // an e5m2 operand: same kernel, other MMA types (WF = weights, XF = activations)
+        const int f = a.b_fmt * 2 + a.a_fmt;
+        if (a.M <= 8) {
+            if (f == 1) return launch_ex(fp8_gemv_mma_kernel<1, 4, 0, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+            if (f == 2) return launch_ex(fp8_gemv_mma_kernel<1, 4, 1, 0>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+            return launch_ex(fp8_gemv_mma_kernel<1, 4, 1, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+        }
+        if (f == 1) return launch_ex(fp8_gemv_mma_kernel<2, 4, 0, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+        if (f == 2) return launch_ex(fp8_gemv_mma_kernel<2, 4, 1, 0>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+        return launch_ex(fp8_gemv_mma_kernel<2, 4, 1, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
+    }
     if (a.M <= 8) {
         if (batch == 4) return launch_ex(fp8_gemv_mma_kernel<1, 4>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);
         if (batch == 1) return launch_ex(fp8_gemv_mma_kernel<1, 1>, dim3(grid), dim3(kMmaThreads), 0, a.st, 1, 1, pdl, p);

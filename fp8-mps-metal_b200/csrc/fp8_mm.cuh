@@ -22,6 +22,7 @@ struct MMArgs {
     void* ws; size_t ws_bytes;
     int store_mc;          // tcgen05 kernel only: C is a multicast address (multimem.st)
     cudaStream_t st;
+    int a_fmt = 0, b_fmt = 0;   // operand formats (FP8B_E4M3FN / FP8B_E5M2); host-side routing only
     int chain_pdl = 0;     // GEMV only: the predecessor on the stream is our own quantise kernel (never writes B),
                            // so launch with PDL and prefetch B before griddepcontrol.wait
 };
@@ -97,6 +98,15 @@ __device__ __forceinline__ void epi_store(const Epi& e, int m, int n, float v) {
 static __device__ __noinline__ float slow_dot_masked(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int K) {
     float s = 0.0f;
     for (int k = 0; k < K; ++k) s = __fmaf_rn(dec1_f32(a[k]), dec1_f32(b[k]), s);
+    return s;
+}
+
+// Same for any operand formats: e4m3fn NaN bytes contribute 0, e5m2 inf / NaN propagate (IEEE).  With an e5m2
+// operand a NaN accumulator may be the right answer; this loop then simply reproduces it.
+static __device__ __noinline__ float slow_dot_fmt(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int K,
+                                                  int a_fmt, int b_fmt) {
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s = __fmaf_rn(dec1_fmt_f32(a[k], a_fmt), dec1_fmt_f32(b[k], b_fmt), s);
     return s;
 }
 

@@ -90,18 +90,23 @@ def fp8_scaled_mm(A: torch.Tensor, B: torch.Tensor,
     return lib.fp8_scaled_mm(A, B, scale_a, scale_b)
 
 
+_FORMATS = {"e4m3fn": 0, "e5m2": 1, 0: 0, 1: 1, None: 0,
+            getattr(torch, "float8_e4m3fn", "e4m3fn"): 0, getattr(torch, "float8_e5m2", "e5m2"): 1}
+
+
 def fp8_scaled_mm_fused(A, B, scale_a, scale_b, bias=None, scale_result=None, out_dtype=None,
-                        algo=0, out=None) -> torch.Tensor:
+                        algo=0, out=None, a_format="e4m3fn", b_format="e4m3fn") -> torch.Tensor:
     """`fp8_scaled_mm` with the epilogue the patch applies as separate torch ops
     (fp8_mps_patch.py:95-104: + bias, * scale_result, .to(out_dtype)) fused into the kernel.
     ``out`` may be a row-major (M,N) view with a wider row stride (a column shard of a bigger
-    matrix)."""
+    matrix).  ``a_format`` / ``b_format``: "e4m3fn" (default; the reference codec, NaN bytes count as 0) or
+    "e5m2" (decoded as e5m2 -- the reference mis-decodes such tensors as e4m3fn -- with IEEE inf/NaN)."""
     lib = _get_lib()
     assert A.dtype == torch.uint8 and B.dtype == torch.uint8
     assert A.is_contiguous() and B.is_contiguous()
     assert B.shape[1] == A.shape[1]
     return lib.fp8_scaled_mm_fused(_to_device(A), _to_device(B), scale_a, scale_b, bias, scale_result,
-                                   out_dtype, algo, out)
+                                   out_dtype, algo, out, _FORMATS[a_format], _FORMATS[b_format])
 
 
 def fp8_dequantize(input: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
@@ -117,11 +122,11 @@ def fp8_dequantize(input: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     return lib.fp8_dequantize(input, scale)
 
 
-def fp8_dequantize_to(input: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def fp8_dequantize_to(input: torch.Tensor, dtype: torch.dtype, format="e4m3fn") -> torch.Tensor:
     """FP8 -> float32/float16/bfloat16 exact cast in one pass (what the patch's scenario 3 does
-    in two, fp8_mps_patch.py:213-221)."""
+    in two, fp8_mps_patch.py:213-221).  ``format="e5m2"`` decodes float8_e5m2 bytes (exact, inf/NaN kept)."""
     lib = _get_lib()
-    return lib.fp8_dequantize_to(_to_device(input), dtype)
+    return lib.fp8_dequantize_to(_to_device(input), dtype, _FORMATS[format])
 
 
 def fp8_encode(input: torch.Tensor):
@@ -218,4 +223,4 @@ def fp8_scaled_mm_fast(A: torch.Tensor, B: torch.Tensor,
     if algo == lib.ALGO_GEMV:                      # M <= 16: still honour "fast" = tensor cores if TMA-able
         A16 = (A.shape[1] % 16 == 0) and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
         algo = lib.ALGO_TCGEN05 if A16 else lib.ALGO_GEMV
-    return lib.fp8_scaled_mm_fused(A, B, scale_a, scale_b, None, None, None, algo, None)
+    return lib.fp8_scaled_mm_fused(A, B, scale_a, scale_b, None, None, None, algo, None, 0, 0)

@@ -20,8 +20,8 @@ Deliberate differences from the reference:
     (reference: keyword-only, fp8_mps_patch.py:53);
   * bias, scale_result and out_dtype are fused into the matmul kernel instead of three extra
     elementwise passes (fp8_mps_patch.py:95-104);
-  * float8_e5m2 tensors are NOT intercepted (the reference sends them to its e4m3fn kernels,
-    fp8_mps_patch.py:48-49,65); they go to the original op;
+  * float8_e5m2 operands are decoded AS e5m2 (the reference sends them to its e4m3fn kernels and
+    mis-decodes them, fp8_mps_patch.py:48-49,65); only decode exists: float -> e5m2 stays with torch;
   * FP8 -> float32/bfloat16 is one exact pass, not dequantise-to-fp16 then .to();
   * the VAE-decode tiling (fp8_mps_patch.py:305-440) works around an MPSGraph tensor-size limit
     that CUDA does not have; the symbol is kept and is a no-op.
@@ -94,7 +94,7 @@ def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=
     """
     Drop-in replacement for torch._scaled_mm for FP8 operands on the GPU.
 
-    input: (M, K) activation, uint8 / float8_e4m3fn
+    input: (M, K) activation, uint8 / float8_e4m3fn / float8_e5m2
     other: (K, N) weight, normally column-major so that other.t() is the (N, K) row-major
            layout the kernels take (fp8_mps_patch.py:82-84)
     Result: ((sum_k a*b) * scale_a) * scale_b [+ bias] [* scale_result], cast to out_dtype
@@ -108,9 +108,12 @@ def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=
         kw[name] = value
 
     on_accel = input.device.type == ACCEL
-    is_fp8 = input.dtype in (torch.uint8, _E4M3) and other.dtype in (torch.uint8, _E4M3)
+    fp8_like = (torch.uint8, _E4M3, _E5M2)           # the reference's predicate (fp8_mps_patch.py:64-65)
+    is_fp8 = input.dtype in fp8_like and other.dtype in fp8_like
     if not (on_accel and is_fp8):
         return _original_scaled_mm(input, other, **kw)
+    a_fmt = 1 if input.dtype == _E5M2 else 0         # uint8 is taken as e4m3fn, like the reference
+    b_fmt = 1 if other.dtype == _E5M2 else 0
 
     a_u8 = input if input.dtype == torch.uint8 else input.view(torch.uint8)
     b_u8 = other if other.dtype == torch.uint8 else other.view(torch.uint8)
@@ -125,7 +128,7 @@ def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=
         sb = torch.ones(1, device=input.device)
 
     return _kernels().fp8_scaled_mm_fused(a_u8, w, sa, sb, bias=kw["bias"], scale_result=kw["scale_result"],
-                                          out_dtype=kw["out_dtype"])
+                                          out_dtype=kw["out_dtype"], a_format=a_fmt, b_format=b_fmt)
 
 
 # --------------------------------------------------------------------------- Tensor.to
@@ -184,8 +187,9 @@ def _metal_tensor_to(self, *args, **kwargs):
                 return self
             if dst_fp8:
                 return self.view(torch.uint8).view(dtype)
-            if self.dtype == _E4M3 and dtype in (torch.float32, torch.float16, torch.bfloat16):
-                return _kernels().fp8_dequantize_to(self.view(torch.uint8), dtype)
+            if dtype in (torch.float32, torch.float16, torch.bfloat16):
+                return _kernels().fp8_dequantize_to(self.view(torch.uint8), dtype,
+                                                    format="e5m2" if self.dtype == _E5M2 else "e4m3fn")
 
     return _original_tensor_to(self, *args, **kwargs)
 

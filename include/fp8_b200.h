@@ -107,6 +107,21 @@ FP8B_API int fp8b_dequant_f16(const uint8_t* in, void* out_f16, size_t n, const 
 FP8B_API int fp8b_dequant(const uint8_t* in, void* out, int out_dtype, size_t n, void* stream);
 
 /*
+ * FP8 operand formats.  Every entry point without a format argument takes e4m3fn, the only format the reference has
+ * kernels for.  The reference's patch also ACCEPTS float8_e5m2 tensors (fp8_mps_patch.py:48-49,65) but decodes
+ * them with the e4m3fn codec, i.e. wrongly; the *_fmt entry points decode e5m2 by its own definition (the upper
+ * byte of an IEEE binary16: exact, +-inf and NaN preserved -- PyTorch's cast).  Decode only: there is no e5m2 encoder.
+ */
+enum fp8b_format {
+    FP8B_E4M3FN = 0,
+    FP8B_E5M2 = 1
+};
+
+/* fp8b_dequant / fp8b_dequant_f16 for either format.  scale (nullable) is allowed for FP8B_F16 output only. */
+FP8B_API int fp8b_dequant_fmt(const uint8_t* in, int in_format, void* out, int out_dtype, size_t n, const float* scale,
+                     void* stream);
+
+/*
  * {f32,f16,bf16} -> FP8 encode.  Replaces float_to_fp8_kernel (fp8_matmul.metal:228-236) and the
  * host-side fp32 up-conversion / pre-scale passes of fp8_encode and fp8_quantize
  * (fp8_mps_native.py:127-155, :170-187):
@@ -187,6 +202,19 @@ FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out
                    const float* scale_result,
                    void* workspace, size_t workspace_bytes,
                    int algo, void* stream);
+
+/*
+ * fp8b_scaled_mm with per-operand formats.  e4m3fn NaN bytes contribute 0 (the reference kernels' rule); e5m2
+ * operands follow IEEE arithmetic (inf and NaN propagate into the fp32 sum).  M <= 16 runs the warp-MMA GEMV
+ * (all four type pairs), larger M the tcgen05 GEMM (formats are two bits of the instruction descriptor).
+ */
+FP8B_API int fp8b_scaled_mm_fmt(const uint8_t* A, int a_format, const uint8_t* B, int b_format, void* C, int out_dtype,
+                       int M, int N, int K, int64_t ldc,
+                       const float* scale_a, int scale_a_len,
+                       const float* scale_b, int scale_b_len,
+                       const void* bias, int bias_dtype,
+                       const float* scale_result,
+                       int algo, void* stream);
 
 /*
  * Linear layer with DYNAMIC per-row activation quantisation: fp8_quantize (per row) -> _scaled_mm in one call,

@@ -56,6 +56,11 @@ def capi():
     L.fp8b_scaled_mm_workspace_bytes.argtypes = [i32, i32, i32]
     L.fp8b_scaled_mm_select.restype = i32
     L.fp8b_scaled_mm_select.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64]
+    if hasattr(L, "fp8b_scaled_mm_fmt") or not os.environ.get("FP8B_LIB"):
+        L.fp8b_scaled_mm_fmt.restype = i32
+        L.fp8b_scaled_mm_fmt.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp, i32, vp]
+        L.fp8b_dequant_fmt.restype = i32
+        L.fp8b_dequant_fmt.argtypes = [vp, i32, vp, i32, sz, vp, vp]
     if hasattr(L, "fp8b_encode_batch") or not os.environ.get("FP8B_LIB"):
         L.fp8b_encode_batch.restype = i32
         L.fp8b_encode_batch.argtypes = [vp, i32, i32, vp]

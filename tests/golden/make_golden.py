@@ -17,7 +17,11 @@ fp8_dequantize) are produced by running the reference's host arithmetic
 (fp8_mps_native.py:121-122, :174-189) with torch CPU ops and the spec encoder in
 place of the kernel launch.
 
-Outputs (committed):  codec_golden.npz, host_golden.npz, kat.json
+float8_e5m2 has no codec in the reference (it mis-routes e5m2 tensors into the e4m3fn kernels); its
+decode table is pinned to PyTorch's own CPU cast, the comparison target the reference itself uses for casts
+(test_mps_vs_cpu.py:308):  e5m2_golden.npz.
+
+Outputs (committed):  codec_golden.npz, host_golden.npz, e5m2_golden.npz, kat.json
 This script never imports oracle/ -- the fixtures are independent of it.
 """
 
@@ -170,6 +174,13 @@ def main():
     kat["torch_cpu_bytes"] = tc
     with open(os.path.join(HERE, "kat.json"), "w") as f:
         json.dump(kat, f, indent=1)
+
+    # ---- float8_e5m2 decode: torch CPU cast of all 256 bytes, as fp32 bit patterns (NaN payloads included)
+    e5 = torch.arange(256, dtype=torch.int32).to(torch.uint8).view(torch.float8_e5m2)
+    np.savez_compressed(os.path.join(HERE, "e5m2_golden.npz"),
+                        decode_f32_bits=e5.to(torch.float32).view(torch.int32).numpy().astype(np.uint32),
+                        decode_f16_bits=e5.to(torch.float16).view(torch.int16).numpy().view(np.uint16),
+                        decode_bf16_bits=e5.to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16))
     print("wrote", os.listdir(HERE))
 
 

@@ -325,3 +325,36 @@ def test_casts_under_pdl_see_fresh_data():
         assert torch.equal(qq, qq_ref) and torch.equal(inv, inv_ref), f"iteration {it} (quantize)"
     xs = x[:70001].float().cpu()
     assert np.array_equal(q[:70001].cpu().numpy(), c_oracle.encode(xs.numpy()))
+
+
+# ------------------------------------------------------------------ float8_e5m2 decode
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_e5m2_decode_all_patterns_and_sizes(dtype):
+    """e5m2 -> wide against the oracle table (pinned to torch's CPU cast): bit-exact for non-NaN, NaN stays NaN;
+    vector body, ragged tail and the unaligned scalar path."""
+    L = capi()
+    table = o.decode_e5m2(np.arange(256, dtype=np.uint8))
+    for n, off in ((256, 0), (7, 0), (4099, 0), ((1 << 20) + 5, 0), (70001, 3)):
+        rng = np.random.default_rng(n)
+        b = np.arange(256, dtype=np.uint8) if n == 256 else rng.integers(0, 256, n + off, dtype=np.uint8)
+        src = torch.from_numpy(b).to(DEV)
+        out = torch.empty(n, dtype=dtype, device=DEV)
+        rc = L.fp8b_dequant_fmt(src.data_ptr() + off, 1, p(out), dt_code(dtype), n, None, stream_ptr())
+        assert rc == 0, L.fp8b_status_string(rc)
+        got = to_np(out)
+        ref = table[b[off:off + n]]
+        nan = np.isnan(ref)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+    # same as torch's own cast on the device, and through the patched Tensor.to
+    import fp8_mps_patch
+    e5 = torch.arange(256, dtype=torch.int32).to(torch.uint8).to(DEV).view(torch.float8_e5m2)
+    want = e5.to(dtype)
+    fp8_mps_patch.install()
+    try:
+        got_t = e5.to(dtype)
+    finally:
+        fp8_mps_patch.uninstall()
+    assert torch.equal(torch.nan_to_num(got_t.float(), nan=123.0), torch.nan_to_num(want.float(), nan=123.0))
+    assert L.fp8b_dequant_fmt(p(src), 2, p(out), dt_code(dtype), 4, None, stream_ptr()) == -1      # unknown format

@@ -471,3 +471,75 @@ def test_dynamic_linear_large_m(M, K, N, xdt, odt):
     _check(y, ref, odt, what=f"dynamic linear M{M}")
     with pytest.raises(RuntimeError):
         fp8_mps_native.fp8_linear_dynamic(x.to(DEV), torch.from_numpy(W).to(DEV), torch.from_numpy(sb), None, odt, single_kernel=True)
+
+
+# ------------------------------------------------------------------ float8_e5m2 operands
+
+def _rand_e5m2(shape, seed, special=False):
+    rng = np.random.default_rng(seed)
+    b = rng.integers(0, 256, shape, dtype=np.uint8)
+    e = b & 0x7C
+    b[e == 0x7C] = 0x3C                                   # no inf / NaN ...
+    b[(b & 0x7F) >= 0x58] = 0x41                          # ... and |v| < 128 so fp32 sums of products stay finite
+    if special:
+        b.reshape(-1)[5] = 0x7C                           # +inf
+        b.reshape(-1)[-3] = 0x7E                          # NaN
+    return b
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 4096, 512), (4, 2048, 300), (16, 1024, 129), (3, 1000, 40),
+                                   (256, 1024, 512), (130, 2048, 384), (33, 520, 70)])
+@pytest.mark.parametrize("fa,fb", [("e5m2", "e4m3fn"), ("e4m3fn", "e5m2"), ("e5m2", "e5m2")])
+def test_e5m2_operands(M, K, N, fa, fb):
+    """`_scaled_mm` with float8_e5m2 operands decoded as e5m2 (the reference mis-decodes them as e4m3fn):
+    warp-MMA GEMV for M <= 16 (generic kernel when K % 16 != 0), tcgen05 GEMM above (SIMT when not TMA-able)."""
+    import fp8_mps_native
+    A = _rand_e5m2((M, K), 1 + M) if fa == "e5m2" else _rand_fp8((M, K), 1 + M)
+    B = _rand_e5m2((N, K), 2 + N) if fb == "e5m2" else _rand_fp8((N, K), 2 + N)
+    sa = np.array([2.0 ** -6], dtype=np.float32)
+    sb = (np.random.default_rng(N).random(N).astype(np.float32) + 0.5) * 2.0 ** -6
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(K))
+    for odt in (None, torch.bfloat16):
+        y = fp8_mps_native.fp8_scaled_mm_fused(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa),
+                                               torch.from_numpy(sb), bias.to(DEV), None, odt, a_format=fa, b_format=fb)
+        ref = o.scaled_mm(A, B, sa, sb, to_np(bias), None, dt_name(odt), a_format=fa, b_format=fb)
+        _check(y, ref, odt, what=f"e5m2 {fa}x{fb} M{M} K{K} N{N}")
+
+
+@pytest.mark.parametrize("M,K,N", [(2, 1024, 64), (128, 1024, 256)])
+def test_e5m2_inf_nan_propagate_and_e4m3_nan_is_zero(M, K, N):
+    """IEEE semantics for e5m2 operands (inf / NaN reach the output), reference semantics for e4m3fn ones
+    (0x7F / 0xFF contribute 0) -- in the same product."""
+    import fp8_mps_native
+    A = _rand_fp8((M, K), 3)
+    A[1, 7] = 0x7F                                       # e4m3fn NaN byte -> 0
+    B = _rand_e5m2((N, K), 4)
+    B[5, 9] = 0x7C                                       # +inf in weight row 5
+    B[6, 3] = 0x7E                                       # NaN in weight row 6
+    one = np.ones(1, dtype=np.float32)
+    y = fp8_mps_native.fp8_scaled_mm_fused(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(one),
+                                           torch.from_numpy(one), None, None, None, a_format="e4m3fn", b_format="e5m2")
+    got = y.cpu().numpy()
+    ref = o.scaled_mm(A, B, one, one, None, None, "f32", a_format="e4m3fn", b_format="e5m2")
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(np.isinf(got), np.isinf(ref))
+    assert np.isnan(got[:, 6]).all() and not np.isfinite(got[:, 5]).any()
+    fin = np.isfinite(ref)
+    assert o.rel_rmse(got[fin], ref[fin]) < 5e-6
+
+
+def test_e5m2_through_patched_scaled_mm():
+    """torch._scaled_mm with a float8_e5m2 operand after install(): routed with the e5m2 decode."""
+    import fp8_mps_patch
+    M, K, N = 8, 512, 96
+    A = _rand_e5m2((M, K), 9)
+    W = _rand_fp8((N, K), 10)
+    a = torch.from_numpy(A).to(DEV).view(torch.float8_e5m2)
+    w = torch.from_numpy(W).to(DEV).view(torch.float8_e4m3fn)
+    sa = torch.tensor([0.25], device=DEV); sb = torch.tensor([0.5], device=DEV)
+    fp8_mps_patch.install()
+    try:
+        y = torch._scaled_mm(a, w.t(), sa, sb, None, None, torch.float32)
+    finally:
+        fp8_mps_patch.uninstall()
+    ref = o.scaled_mm(A, W, np.array([0.25], np.float32), np.array([0.5], np.float32), None, None, "f32", a_format="e5m2")
+    _check(y, ref, None, what="patched e5m2")

@@ -152,3 +152,19 @@ def test_epilogue_order_and_out_dtypes():
     assert np.all((bf.view(np.uint32) & 0xFFFF) == 0)
     h = o.scaled_mm(A, B, sa, sb, out_dtype="f16")
     assert np.array_equal(h, base.astype(np.float16).astype(np.float32))
+
+
+def test_e5m2_decode_table_matches_torch_cast():
+    """float8_e5m2 has no codec in the reference; the oracle's table is pinned to PyTorch's CPU cast
+    (tests/golden/e5m2_golden.npz): bit-exact for the 250 non-NaN bytes, NaN for the six NaN bytes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "e5m2_golden.npz"))
+    ref = g["decode_f32_bits"].view(np.float32)
+    ours = o.decode_e5m2(np.arange(256, dtype=np.uint8))
+    nan = np.isnan(ref)
+    assert nan.sum() == 6 and np.array_equal(np.isnan(ours), nan)
+    assert np.array_equal(ours[~nan].view(np.uint32), ref[~nan].view(np.uint32))
+    assert ours[0x7C] == np.inf and ours[0xFC] == -np.inf and ours[0x7B] == 57344.0 and ours[0x01] == 2.0 ** -16
+    # every value is exactly representable in fp16 and bf16
+    assert np.array_equal(g["decode_f16_bits"][~nan], (np.arange(256, dtype=np.uint16) << 8)[~nan])
+    assert np.array_equal(o.f32_to_bf16_bits(ours[~nan]), g["decode_bf16_bits"][~nan])
