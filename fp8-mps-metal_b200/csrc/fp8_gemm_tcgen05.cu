@@ -699,11 +699,17 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = a.st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int nattr = 0;
+    if (CG > 1) {
+        attr[nattr].id = cudaLaunchAttributeClusterDimension;
+        attr[nattr].val.clusterDim.x = CG; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+        ++nattr;
+    }
+    // (Programmatic dependent launch was measured here too -- prologue overlapped with the predecessor's tail -- and
+    // changed nothing: 104.17 vs 104.12 us back to back.  The kernel is power-limited, idle gaps only buy clock.)
     cfg.attrs = attr;
-    cfg.numAttrs = CG > 1 ? 1 : 0;
+    cfg.numAttrs = nattr;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG>, tmap_a, tmap_b, p);
     if (e != cudaSuccess) return cuda_fail(e);
     if (p.dbg) {

@@ -56,7 +56,9 @@ struct GemvXqParams {
 
 __device__ __forceinline__ uint4 ldg_w_v4(const uint8_t* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    // coherent (no .nc): every launch uses programmatic dependent launch, and ptxas hoists non-coherent loads above
+    // griddepcontrol.wait -- B may have been written by the kernel just before (an encode, a transfer)
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
@@ -472,7 +474,7 @@ static int launch_gemv_mt(const GemvParams& p, int S, size_t smem, cudaStream_t 
 {
     static std::atomic<int> attr_done[64];
     if (int rc = ensure_max_smem(fp8_gemv_kernel<MT, U>, kGemvMaxSmem, attr_done)) return rc;
-    const bool pdl = p.static_b != 0;
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;   // always: resident while the predecessor drains
     return launch_ex(fp8_gemv_kernel<MT, U>, dim3((p.N + kGemvWarps - 1) / kGemvWarps, S, 1), dim3(kGemvThreads, 1, 1),
                      smem, st, 1, S, pdl, p);
 }
@@ -482,7 +484,7 @@ static int launch_gemv_xq_mt(const GemvXqParams& xp, int S, size_t smem, cudaStr
 {
     static std::atomic<int> attr_done[64];
     if (int rc = ensure_max_smem(fp8_gemv_xq_kernel<MT, U>, kGemvMaxSmem, attr_done)) return rc;
-    const bool pdl = xp.g.static_b != 0;
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
     return launch_ex(fp8_gemv_xq_kernel<MT, U>, dim3((xp.g.N + kGemvWarps - 1) / kGemvWarps, S, 1), dim3(kGemvThreads, 1, 1),
                      smem, st, 1, S, pdl, xp);
 }

@@ -36,7 +36,9 @@ struct GemvMmaParams {
 
 __device__ __forceinline__ uint4 ldg_stream16(const uint8_t* p) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    // coherent (no .nc): every launch uses programmatic dependent launch, and ptxas hoists non-coherent loads above
+    // griddepcontrol.wait -- B may have been written by the kernel just before (an encode, a transfer)
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
@@ -177,7 +179,7 @@ int launch_gemv_mma(const MMArgs& a)
     p.k_per_warp = (((a.K + kMmaWarps - 1) / kMmaWarps) + 63) & ~63;
     p.epi = make_epi(a);
     p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && (a.chain_pdl || g_opt_static_weights.load(std::memory_order_relaxed))) ? 1 : 0;
-    const bool pdl = p.static_b != 0;      // without static weights PDL only hides launch latency, which graphs already do
+    const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;   // always: resident while the predecessor drains
     const int grid = (a.N + kMmaRows - 1) / kMmaRows;
     const int batch = tune_int("FP8B_GEMV_BATCH", 4);
     if (a.a_fmt | a.b_fmt) {                // an e5m2 operand: same kernel, other MMA types (WF = weights, XF = activations)
