@@ -704,6 +704,7 @@ def main():
                                                                peaks, args.steps, args.warmup, rotation=32)
             sub["C3_gemv_M4_K4096_N4096_bias_bf16"] = bench_gemv_cfg(torch, L, C3, C3_BYTES, torch.bfloat16, True, gen,
                                                                      dev, peaks, args.steps, args.warmup, rotation=32)
+            sub["C1_gemv_M1_K4096_N4096_f16"]["roofline"]["traffic"] = profile_traffic("gemv1k4")
             sub["C3_gemv_M4_K4096_N4096_bias_bf16"]["roofline"]["traffic"] = profile_traffic("gemv4")
         except Exception as e:
             sub["gemv_error"] = repr(e)
