@@ -74,8 +74,10 @@ FP8B_API uint64_t fp8b_launch_count(void);
 
 /*
  * Library options (process-wide, may be changed between calls).
- *   FP8B_OPT_PDL             1 (default): programmatic dependent launch may be used (it is used when
- *                            FP8B_OPT_STATIC_WEIGHTS is on).  0: plain stream order always.
+ *   FP8B_OPT_PDL             1 (default): the GEMV and cast kernels are launched with programmatic dependent launch:
+ *                            they become resident while their predecessor on the stream drains and wait
+ *                            (griddepcontrol.wait) before their first global access, so results never depend on
+ *                            it.  0: plain stream order always.
  *   FP8B_OPT_STATIC_WEIGHTS  0 (default).  1: the caller promises that the B operand (the weight matrix) of
  *                            fp8b_scaled_mm is never written by work still in flight on the stream.  The GEMV
  *                            kernels then start streaming B BEFORE waiting for the predecessor (only A, the
