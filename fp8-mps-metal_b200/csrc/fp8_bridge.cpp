@@ -122,6 +122,89 @@ torch::Tensor fp8_scaled_mm_fused(torch::Tensor A, torch::Tensor B, torch::Tenso
     return C;
 }
 
+// ---- torch._scaled_mm as the patch sees it, in one C++ call --------------------------------------
+// fp8_mps_patch._metal_scaled_mm used to do the dtype views, the transpose check and the scale conversions as
+// separate Python-level tensor ops (~6 us of host time per call, more than a decode GEMV's kernel time); this does
+// the same on raw strides and pointers.  input: (M,K) uint8 / float8_e4m3fn / float8_e5m2; other: (K,N), normally
+// column-major so that its memory IS the (N,K) row-major weight (fp8_mps_patch.py:82-84).
+namespace {
+
+int format_of(const torch::Tensor& t)
+{
+    return t.scalar_type() == at::kFloat8_e5m2 ? FP8B_E5M2 : FP8B_E4M3FN;     // uint8 is taken as e4m3fn (reference)
+}
+
+bool is_fp8_like(const torch::Tensor& t)
+{
+    const auto st = t.scalar_type();
+    return st == at::kByte || st == at::kFloat8_e4m3fn || st == at::kFloat8_e5m2;
+}
+
+// float32 device pointer for a scale tensor without touching it when it already is one
+const float* scale_ptr(const c10::optional<torch::Tensor>& s, const torch::Device& dev, torch::Tensor& keep, int64_t& len)
+{
+    if (!s.has_value() || !s->defined()) {
+        keep = torch::ones({1}, torch::TensorOptions().dtype(torch::kFloat32).device(dev));   // fp8_mps_patch.py:87-90
+    } else if (s->device() == dev && s->scalar_type() == at::kFloat && s->is_contiguous()) {
+        keep = *s;
+    } else {
+        keep = as_device_f32(*s, dev);
+    }
+    len = keep.numel();
+    return keep.data_ptr<float>();
+}
+
+}  // namespace
+
+torch::Tensor scaled_mm_patch(torch::Tensor input, torch::Tensor other, c10::optional<torch::Tensor> scale_a,
+                              c10::optional<torch::Tensor> scale_b, c10::optional<torch::Tensor> bias,
+                              c10::optional<torch::Tensor> scale_result, c10::optional<at::ScalarType> out_dtype)
+{
+    TORCH_CHECK(is_fp8_like(input) && is_fp8_like(other), "operands must be uint8 / float8_e4m3fn / float8_e5m2");
+    TORCH_CHECK(input.is_cuda() && other.is_cuda() && input.device() == other.device(), "operands must be CUDA tensors on one device");
+    TORCH_CHECK(input.dim() == 2 && other.dim() == 2 && input.size(1) == other.size(0), "K dimension mismatch between A and B");
+    const int64_t M = input.size(0), K = input.size(1), N = other.size(1);
+    TORCH_CHECK(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "extent too large");
+    const auto dev = input.device();
+    c10::cuda::CUDAGuard guard(dev);
+
+    torch::Tensor a = input.is_contiguous() ? input : input.contiguous();
+    // (N,K) row-major view of `other`: free when other is column-major, one copy otherwise (fp8_mps_patch.py:84)
+    torch::Tensor b = (other.stride(0) == 1 && (other.stride(1) == K || N == 1)) ? other : other.t().contiguous();
+
+    torch::Tensor sa_t, sb_t, sr_t, bias_t;
+    int64_t sa_len = 0, sb_len = 0;
+    const float* sa = scale_ptr(scale_a, dev, sa_t, sa_len);
+    const float* sb = scale_ptr(scale_b, dev, sb_t, sb_len);
+    TORCH_CHECK(sa_len == 1 || sa_len == M, "scale_a must have 1 or M elements");
+    TORCH_CHECK(sb_len == 1 || sb_len == N, "scale_b must have 1 or N elements");
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = (bias->device() == dev && bias->is_contiguous()) ? *bias : bias->to(dev).contiguous();
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    const float* sr = nullptr;
+    if (scale_result.has_value() && scale_result->defined()) {
+        int64_t sr_len = 0;
+        sr = scale_ptr(scale_result, dev, sr_t, sr_len);
+        TORCH_CHECK(sr_len == 1, "scale_result must have 1 element");
+    }
+    const at::ScalarType odt = out_dtype.value_or(at::kFloat);          // out_dtype=None -> fp32 (fp8_mps_patch.py:103)
+    torch::Tensor C = torch::empty({M, N}, torch::TensorOptions().dtype(odt).device(dev));
+    if (M == 0 || N == 0) return C;
+    const int rc = fp8b_scaled_mm_fmt(static_cast<const uint8_t*>(a.data_ptr()), format_of(input),
+                                      static_cast<const uint8_t*>(b.data_ptr()), format_of(other), C.data_ptr(),
+                                      to_fp8b_dtype(odt), (int)M, (int)N, (int)K, N, sa, (int)sa_len, sb, (int)sb_len,
+                                      bias_ptr, bias_dt, sr, FP8B_MM_AUTO, current_stream());
+    check_status(rc, "fp8b_scaled_mm");
+    return C;
+}
+
 // ---- the reference bridge's three ops (fp8_bridge.cpp:165, :265, :312) ------------------------
 torch::Tensor fp8_scaled_mm(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b)
 {
@@ -371,6 +454,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias") = py::none(),
           py::arg("scale_result") = py::none(), py::arg("out_dtype") = py::none(), py::arg("algo") = 0,
           py::arg("out") = py::none(), py::arg("a_format") = 0, py::arg("b_format") = 0);
+    m.def("scaled_mm_patch", &scaled_mm_patch, "torch._scaled_mm(input, other, ...) for FP8 operands, whole wrapper in C++",
+          py::arg("input"), py::arg("other"), py::arg("scale_a") = py::none(), py::arg("scale_b") = py::none(),
+          py::arg("bias") = py::none(), py::arg("scale_result") = py::none(), py::arg("out_dtype") = py::none());
     m.def("fp8_scaled_mm_multicast", &fp8_scaled_mm_multicast,
           "FP8 scaled matmul storing through an NVSwitch multicast address (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out_dtype"),

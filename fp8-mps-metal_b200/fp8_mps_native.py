@@ -109,6 +109,13 @@ def fp8_scaled_mm_fused(A, B, scale_a, scale_b, bias=None, scale_result=None, ou
                                    out_dtype, algo, out, _FORMATS[a_format], _FORMATS[b_format])
 
 
+def scaled_mm_patch(input, other, scale_a=None, scale_b=None, bias=None, scale_result=None, out_dtype=None):
+    """`torch._scaled_mm(input, other, ...)` for FP8 operands on the GPU, the whole wrapper in one extension call
+    (what fp8_mps_patch._metal_scaled_mm dispatches to).  input (M,K), other (K,N) uint8 / float8_e4m3fn /
+    float8_e5m2; scales default to 1 (fp8_mps_patch.py:87-90); out_dtype None -> float32 (:103-104)."""
+    return _get_lib().scaled_mm_patch(input, other, scale_a, scale_b, bias, scale_result, out_dtype)
+
+
 def fp8_dequantize(input: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """
     FP8 -> half dequantization (reference: fp8_mps_native.py:98-124).

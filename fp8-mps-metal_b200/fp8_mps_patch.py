@@ -112,23 +112,11 @@ def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=
     is_fp8 = input.dtype in fp8_like and other.dtype in fp8_like
     if not (on_accel and is_fp8):
         return _original_scaled_mm(input, other, **kw)
-    a_fmt = 1 if input.dtype == _E5M2 else 0         # uint8 is taken as e4m3fn, like the reference
-    b_fmt = 1 if other.dtype == _E5M2 else 0
-
-    a_u8 = input if input.dtype == torch.uint8 else input.view(torch.uint8)
-    b_u8 = other if other.dtype == torch.uint8 else other.view(torch.uint8)
-    if not a_u8.is_contiguous():
-        a_u8 = a_u8.contiguous()
-    w = b_u8.t().contiguous()                       # (N, K) row-major; a free view for column-major `other`
-
-    sa, sb = kw["scale_a"], kw["scale_b"]
-    if sa is None:
-        sa = torch.ones(1, device=input.device)     # default scales (fp8_mps_patch.py:87-90)
-    if sb is None:
-        sb = torch.ones(1, device=input.device)
-
-    return _kernels().fp8_scaled_mm_fused(a_u8, w, sa, sb, bias=kw["bias"], scale_result=kw["scale_result"],
-                                          out_dtype=kw["out_dtype"], a_format=a_fmt, b_format=b_fmt)
+    # dtype views, the (N,K) view of `other`, default scales (fp8_mps_patch.py:82-90) and the fused epilogue
+    # (:95-104) all happen inside one extension call: the Python-level version of this cost more host time than
+    # a decode GEMV takes on the GPU.  float8_e5m2 operands are decoded as e5m2; uint8 is taken as e4m3fn.
+    return _kernels().scaled_mm_patch(input, other, kw["scale_a"], kw["scale_b"], kw["bias"], kw["scale_result"],
+                                      kw["out_dtype"])
 
 
 # --------------------------------------------------------------------------- Tensor.to
