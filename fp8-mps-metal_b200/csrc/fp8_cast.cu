@@ -424,6 +424,78 @@ quantize_rows_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, flo
         rout[i] = enc1_f32(__fmul_rn(load_wide_scalar<IN>(rin, i), s));
 }
 
+// Register-resident variant for rows that fit in registers: TPR threads per row (32: a warp per row, 8 rows per
+// CTA, no barrier at all; ... 256: a CTA per row), each thread holding V 16-byte vectors.  The row is read from HBM
+// ONCE -- amax, scale and encode all work on the registers -- and every thread has V independent loads in flight.
+// Same arithmetic as quantize_rows_kernel, so the bytes and scales are identical.
+template <int IN, int V, int TPR>
+__global__ void __launch_bounds__(kCastThreads)
+quantize_rows_reg_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, float* __restrict__ inv_scale,
+                         int rows, int nvec)
+{
+    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    constexpr int ESZ = (IN == FP8B_F32) ? 4 : 2;
+    constexpr int RPC = kCastThreads / TPR;                  // rows per CTA
+    pdl_launch_dependents();
+    const int t = threadIdx.x % TPR;
+    const int row = blockIdx.x * RPC + threadIdx.x / TPR;
+    const bool row_ok = row < rows;
+    const size_t cols = (size_t)nvec * EPV;
+    const uint8_t* rin = reinterpret_cast<const uint8_t*>(in) + (size_t)(row_ok ? row : 0) * cols * ESZ;
+    uint4 w[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int v = t + j * TPR;
+        w[j] = (row_ok && v < nvec) ? ldg_stream_v4(rin + (size_t)v * 16) : make_uint4(0, 0, 0, 0);
+    }
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const uint32_t* p = &w[j].x;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (IN == FP8B_F32) m = max(m, p[i] & 0x7FFFFFFFu);
+            else if (IN == FP8B_BF16) { m = max(m, (p[i] << 16) & 0x7FFFFFFFu); m = max(m, p[i] & 0x7FFF0000u); }
+            else {
+                float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p[i]));
+                m = max(m, __float_as_uint(f.x) & 0x7FFFFFFFu);
+                m = max(m, __float_as_uint(f.y) & 0x7FFFFFFFu);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if (TPR > 32) {                                           // TPR / 32 warps share a row: combine them
+        constexpr int WPR = TPR / 32;
+        __shared__ uint32_t sm[kCastThreads / 32];
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+        __syncthreads();
+        const int w0 = (threadIdx.x / TPR) * WPR;
+        m = 0;
+#pragma unroll
+        for (int i = 0; i < WPR; ++i) m = max(m, sm[w0 + i]);
+    }
+    float s = 1.0f;
+    if ((threadIdx.x & 31) == 0) {                            // one double division per warp, broadcast below
+        const float amax = __uint_as_float(m);
+        const double scale = (amax > 0.0f) ? 448.0 / (double)amax : 1.0;     // native.py:175-176, in double
+        s = (float)scale;
+        if (row_ok && t == 0) inv_scale[row] = (float)(1.0 / scale);          // native.py:189
+    }
+    s = __shfl_sync(0xFFFFFFFFu, s, 0);
+    uint8_t* rout = out + (size_t)(row_ok ? row : 0) * cols;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int v = t + j * TPR;
+        if (row_ok && v < nvec) {
+            uint32_t o0, o1;
+            encode_vec<IN, true>(w[j], s, o0, o1);
+            if (IN == FP8B_F32) *reinterpret_cast<uint32_t*>(rout + (size_t)v * 4) = o0;
+            else *reinterpret_cast<uint2*>(rout + (size_t)v * 8) = make_uint2(o0, o1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Batched casts: MANY tensors in ONE launch (a whole checkpoint's weights; the reference converts them one
 // .to() at a time, fp8_mps_patch.py:143-230).  A per-tensor launch pays ~3 us of ramp + drain on a ~18 us
@@ -762,6 +834,37 @@ extern "C" int fp8b_quantize_rows(const void* in, int in_dtype, int rows, size_t
     const size_t epv = 16 / esz;
     // vector path: every row start 16-byte aligned on the wide side and epv-byte aligned on the fp8 side
     const int vec_ok = aligned(in, 16) && aligned(out, epv) && ((cols * esz) % 16 == 0) ? 1 : 0;
+    // rows that fit in registers: one HBM read, no second pass (quantize_rows_reg_kernel)
+    if (vec_ok && cols % epv == 0 && cols / epv <= 256 * 8 && cols > 0) {
+        const int nvec = (int)(cols / epv);
+        int rc = FP8B_OK;
+#define FP8B_ROWS_REG(IN, V, TPR) \
+        quantize_rows_reg_kernel<IN, V, TPR><<<(rows + (kCastThreads / TPR) - 1) / (kCastThreads / TPR), kCastThreads, 0, st>>>( \
+            in, out, inv_scale_out, rows, nvec)
+        // Few vectors per thread (V <= 4: registers stay low, many warps resident) and as many threads per row as
+        // that needs; when there are too few rows to fill the GPU with warps, a whole CTA per row instead.
+        const bool few_rows = (size_t)rows * 64 < (size_t)device_info().sm_count * 2048;
+#define FP8B_ROWS_PICK(IN) \
+        do { \
+            if (few_rows || nvec > 128 * 4) { \
+                if (nvec <= 256) FP8B_ROWS_REG(IN, 1, 256); \
+                else if (nvec <= 512) FP8B_ROWS_REG(IN, 2, 256); \
+                else if (nvec <= 1024) FP8B_ROWS_REG(IN, 4, 256); \
+                else FP8B_ROWS_REG(IN, 8, 256); \
+            } \
+            else if (nvec <= 32 * 2) FP8B_ROWS_REG(IN, 2, 32); \
+            else if (nvec <= 32 * 4) FP8B_ROWS_REG(IN, 4, 32); \
+            else if (nvec <= 64 * 4) FP8B_ROWS_REG(IN, 4, 64); \
+            else FP8B_ROWS_REG(IN, 4, 128); \
+        } while (0)
+        if (in_dtype == FP8B_F32) FP8B_ROWS_PICK(FP8B_F32);
+        else if (in_dtype == FP8B_F16) FP8B_ROWS_PICK(FP8B_F16);
+        else FP8B_ROWS_PICK(FP8B_BF16);
+#undef FP8B_ROWS_PICK
+#undef FP8B_ROWS_REG
+        (void)rc;
+        return after_launch();
+    }
     if (in_dtype == FP8B_F32) quantize_rows_kernel<FP8B_F32><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
     else if (in_dtype == FP8B_F16) quantize_rows_kernel<FP8B_F16><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
     else quantize_rows_kernel<FP8B_BF16><<<rows, kCastThreads, 0, st>>>(in, out, inv_scale_out, cols, vec_ok);
