@@ -25,6 +25,13 @@ __device__ __forceinline__ uint4 ldg_stream_v4(const void* p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+// 256-bit load (sm_100: LDG.E.256).  For the read+write streams of wide -> fp8, 32-byte loads with 4 per thread
+// in flight measured 6.85 TB/s against 6.0 TB/s for the same bytes in flight as 16-byte loads
+// (profiles/tools/castbw.cu); 256-bit STORES made no difference for fp8 -> wide.
+__device__ __forceinline__ void ldg_stream_v8(const void* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
 __device__ __forceinline__ uint2 ldg_stream_v2(const void* p) {
     uint2 r;
     asm volatile("ld.global.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
@@ -228,35 +235,57 @@ __device__ __forceinline__ float load_wide_scalar(const void* in, size_t i) {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[i]);
 }
 
-template <int IN, bool PRESCALE, int THREADS, int UNROLL>
+// VB = bytes per wide-side vector: 16 (any 16-byte aligned tensor) or 32 (256-bit loads, 32-byte aligned tensors).
+template <int IN, bool PRESCALE, int THREADS, int UNROLL, int VB = 16>
 __device__ __forceinline__ void encode_tile(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t vbegin,
                                             size_t nvec, float s)
 {
     const size_t v0 = vbegin + threadIdx.x;                    // converts vectors [vbegin, min(vbegin + tile, nvec))
-    uint4 w[UNROLL];
+    if (VB == 16) {
+        uint4 w[UNROLL];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-        const size_t v = v0 + (size_t)u * THREADS;
-        w[u] = v < nvec ? ldg_stream_v4(in + v * 16) : make_uint4(0, 0, 0, 0);
-    }
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t v = v0 + (size_t)u * THREADS;
+            w[u] = v < nvec ? ldg_stream_v4(in + v * 16) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-        const size_t v = v0 + (size_t)u * THREADS;
-        if (v < nvec) {
-            uint32_t o0, o1;
-            encode_vec<IN, PRESCALE>(w[u], s, o0, o1);
-            if (IN == FP8B_F32) stg_stream_u32(out + v * 4, o0);
-            else stg_stream_v2(out + v * 8, make_uint2(o0, o1));
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t v = v0 + (size_t)u * THREADS;
+            if (v < nvec) {
+                uint32_t o0, o1;
+                encode_vec<IN, PRESCALE>(w[u], s, o0, o1);
+                if (IN == FP8B_F32) stg_stream_u32(out + v * 4, o0);
+                else stg_stream_v2(out + v * 8, make_uint2(o0, o1));
+            }
+        }
+    } else {
+        uint4 lo[UNROLL], hi[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t v = v0 + (size_t)u * THREADS;
+            lo[u] = hi[u] = make_uint4(0, 0, 0, 0);
+            if (v < nvec) ldg_stream_v8(in + v * 32, lo[u], hi[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t v = v0 + (size_t)u * THREADS;
+            if (v < nvec) {
+                uint32_t o0, o1, o2, o3;
+                encode_vec<IN, PRESCALE>(lo[u], s, o0, o1);
+                encode_vec<IN, PRESCALE>(hi[u], s, o2, o3);
+                if (IN == FP8B_F32) stg_stream_v2(out + v * 8, make_uint2(o0, o2));
+                else stg_stream_v4(out + v * 16, make_uint4(o0, o1, o2, o3));
+            }
         }
     }
 }
 
-template <int IN, bool PRESCALE, int THREADS, int UNROLL>
+template <int IN, bool PRESCALE, int THREADS, int UNROLL, int VB = 16>
 __global__ void __launch_bounds__(THREADS)
 wide_to_fp8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_t n,
                    const float* __restrict__ prescale)
 {
-    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    constexpr int EPV = ((IN == FP8B_F32) ? 4 : 8) * (VB / 16);
     const size_t nvec = n / EPV;
     pdl_launch_dependents();
     pdl_wait();
@@ -264,8 +293,8 @@ wide_to_fp8_kernel(const void* __restrict__ in, uint8_t* __restrict__ out, size_
     const uint8_t* i8 = reinterpret_cast<const uint8_t*>(in);
     TileWalk<THREADS * UNROLL> walk(nvec);
     for (size_t r = 0; r < walk.rounds; ++r)
-        encode_tile<IN, PRESCALE, THREADS, UNROLL>(i8, out, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s);
-    if (walk.rem_begin < walk.rem_end) encode_tile<IN, PRESCALE, THREADS, UNROLL>(i8, out, walk.rem_begin, walk.rem_end, s);
+        encode_tile<IN, PRESCALE, THREADS, UNROLL, VB>(i8, out, (r * gridDim.x + blockIdx.x) * (size_t)(THREADS * UNROLL), nvec, s);
+    if (walk.rem_begin < walk.rem_end) encode_tile<IN, PRESCALE, THREADS, UNROLL, VB>(i8, out, walk.rem_begin, walk.rem_end, s);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = nvec * EPV; i < n; ++i) {
             float f = load_wide_scalar<IN>(in, i);
@@ -512,13 +541,13 @@ struct CastBatch {
     size_t n[kBatchMaxSpans];
 };
 
-template <int IN, int THREADS, int UNROLL>
+template <int IN, int THREADS, int UNROLL, int VB = 16>
 __global__ void __launch_bounds__(THREADS)
 wide_to_fp8_batch_kernel(const __grid_constant__ CastBatch b)
 {
     pdl_launch_dependents();
     pdl_wait();
-    constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
+    constexpr int EPV = ((IN == FP8B_F32) ? 4 : 8) * (VB / 16);
     const uint32_t total = b.tile_end[b.count - 1];
     int span = 0;
     for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
@@ -527,7 +556,7 @@ wide_to_fp8_batch_kernel(const __grid_constant__ CastBatch b)
         const size_t n = b.n[span];
         const uint8_t* in = reinterpret_cast<const uint8_t*>(b.in[span]);
         uint8_t* out = reinterpret_cast<uint8_t*>(b.out[span]);
-        encode_tile<IN, false, THREADS, UNROLL>(in, out, (size_t)(t - t0) * (THREADS * UNROLL), n / EPV, 1.0f);
+        encode_tile<IN, false, THREADS, UNROLL, VB>(in, out, (size_t)(t - t0) * (THREADS * UNROLL), n / EPV, 1.0f);
         if (t + 1 == b.tile_end[span] && threadIdx.x == 0)    // ragged tail of this tensor (< EPV elements)
             for (size_t i = n / EPV * EPV; i < n; ++i) out[i] = enc1_f32(load_wide_scalar<IN>(in, i));
     }
@@ -654,13 +683,18 @@ extern "C" int fp8b_dequant_fmt(const uint8_t* in, int in_format, void* out, int
                  : launch_decode_e5m2<FP8B_F16, false>(in, out, n, nullptr, st);
 }
 
-// wide -> fp8 launch: big tiles = 1024 threads x 4, small = 256 x 4
+// wide -> fp8 launch: big tiles = 512 threads x 4 x 32 B (or 1024 x 4 x 16 B), small = 256 x 4 x 16 B
 template <int IN, bool PRESCALE>
 static int launch_encode_vec(const void* in, uint8_t* out, size_t n, const float* prescale, cudaStream_t st)
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     const CastShape c = cast_shape(n / EPV);
     const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    // big tiles: 512 threads x 4 x 32-byte loads when the tensor allows 256-bit access, else 1024 x 4 x 16 bytes
+    // (256-bit loads pay from ~2^26 elements: +3 % at 2^28, +10 % at 2^32, but -20 % at 2^24 where the kernel is
+    // mostly ramp and the 512-thread CTAs expose less parallelism -- profiles/tools/cast_exp.py)
+    if (c.big && n / EPV >= ((size_t)1 << 23) && aligned(in, 32) && aligned(out, 2 * EPV))
+        return launch_ex(wide_to_fp8_kernel<IN, PRESCALE, 512, 4, 32>, dim3(c.grid), dim3(512), 0, st, 1, 1, pdl, in, out, n, prescale);
     if (c.big) return launch_ex(wide_to_fp8_kernel<IN, PRESCALE, 1024, 4>, dim3(c.grid), dim3(1024), 0, st, 1, 1, pdl, in, out, n, prescale);
     return launch_ex(wide_to_fp8_kernel<IN, PRESCALE, 256, 4>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, prescale);
 }
@@ -709,7 +743,7 @@ namespace {
 // Collects aligned, non-empty spans into CastBatch tables and launches one persistent grid per table.
 // epv: elements per wide-side vector; fp8_in: true for fp8 -> wide.  launch(table, grid, big).
 template <typename LaunchFn, typename SingleFn>
-int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, LaunchFn launch, SingleFn single)
+int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, int big_align_mult, LaunchFn launch, SingleFn single)
 {
     if (count < 0 || (count > 0 && !spans)) return FP8B_ERR_INVALID;
     for (int i = 0; i < count; ++i)
@@ -723,6 +757,13 @@ int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, LaunchFn 
     uint64_t total_vecs = 0;
     for (int i = 0; i < count; ++i) if (spans[i].n && vec_ok(spans[i])) total_vecs += spans[i].n / epv;
     const CastShape shape = cast_shape((size_t)total_vecs);
+    // the big-tile kernel of this direction may need wider alignment (256-bit loads): such spans still convert,
+    // through the single-tensor entry point
+    const bool wide_loads = shape.big && big_align_mult > 1 && total_vecs >= (1ull << 23);
+    const int mult = wide_loads ? big_align_mult : 1;
+    auto table_ok = [&](const fp8b_span& sp) {
+        return aligned(fp8_in ? sp.out : sp.in, 16 * mult) && aligned(fp8_in ? sp.in : sp.out, epv * mult);
+    };
     const uint64_t tile_vecs = shape.big ? 4096 : 1024;
     const uint64_t cap = (uint64_t)device_info().sm_count * (shape.big ? 1 : 4);
     CastBatch b;
@@ -730,14 +771,14 @@ int run_batch(const fp8b_span* spans, int count, int epv, bool fp8_in, LaunchFn 
     uint64_t tiles = 0;
     auto flush = [&]() -> int {
         if (b.count == 0) return FP8B_OK;
-        const int rc = launch(b, (int)(tiles < cap ? tiles : cap), shape.big);
+        const int rc = launch(b, (int)(tiles < cap ? tiles : cap), shape.big ? (wide_loads ? 2 : 1) : 0);
         b.count = 0; tiles = 0;
         return rc;
     };
     for (int i = 0; i < count; ++i) {
         const fp8b_span& sp = spans[i];
         if (sp.n == 0) continue;
-        if (!vec_ok(sp)) {                                             // rare: scalar single-tensor path
+        if (!table_ok(sp)) {                                           // rare: single-tensor path (scalar or 16-byte kernels)
             if (int rc = single(sp)) return rc;
             continue;
         }
@@ -758,6 +799,7 @@ template <int IN>
 int launch_encode_batch(const CastBatch& b, int grid, int big, cudaStream_t st)
 {
     const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;
+    if (big == 2) return launch_ex(wide_to_fp8_batch_kernel<IN, 512, 4, 32>, dim3(grid), dim3(512), 0, st, 1, 1, pdl, b);
     if (big) return launch_ex(wide_to_fp8_batch_kernel<IN, 1024, 4>, dim3(grid), dim3(1024), 0, st, 1, 1, pdl, b);
     return launch_ex(wide_to_fp8_batch_kernel<IN, 256, 4>, dim3(grid), dim3(256), 0, st, 1, 1, pdl, b);
 }
@@ -784,7 +826,7 @@ extern "C" int fp8b_encode_batch(const fp8b_span* spans, int count, int in_dtype
     auto single = [&](const fp8b_span& sp) -> int {
         return fp8b_encode(sp.in, in_dtype, static_cast<uint8_t*>(sp.out), sp.n, nullptr, stream);
     };
-    return run_batch(spans, count, in_dtype == FP8B_F32 ? 4 : 8, false, launch, single);
+    return run_batch(spans, count, in_dtype == FP8B_F32 ? 4 : 8, false, 2, launch, single);
 }
 
 extern "C" int fp8b_dequant_batch(const fp8b_span* spans, int count, int out_dtype, void* stream)
@@ -799,7 +841,7 @@ extern "C" int fp8b_dequant_batch(const fp8b_span* spans, int count, int out_dty
     auto single = [&](const fp8b_span& sp) -> int {
         return fp8b_dequant(static_cast<const uint8_t*>(sp.in), sp.out, out_dtype, sp.n, stream);
     };
-    return run_batch(spans, count, out_dtype == FP8B_F32 ? 4 : 8, true, launch, single);
+    return run_batch(spans, count, out_dtype == FP8B_F32 ? 4 : 8, true, 1, launch, single);
 }
 
 extern "C" int fp8b_amax_scale(const void* in, int in_dtype, size_t n, float* scale_out, float* inv_scale_out,

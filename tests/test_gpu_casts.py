@@ -363,3 +363,38 @@ def test_e5m2_decode_all_patterns_and_sizes(dtype):
         fp8_mps_patch.uninstall()
     assert torch.equal(torch.nan_to_num(got_t.float(), nan=123.0), torch.nan_to_num(want.float(), nan=123.0))
     assert L.fp8b_dequant_fmt(p(src), 2, p(out), dt_code(dtype), 4, None, stream_ptr()) == -1      # unknown format
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_big_tile_paths_256bit_and_128bit(dtype):
+    """Large tensors take the 64 KB-tile kernels: 256-bit loads when the tensor is 32-byte aligned, the 16-byte
+    variant otherwise; both, single and batched, must give the bytes of the (oracle-checked) small-tile path."""
+    L = capi()
+    n = 68 * (1 << 20) + 13                                 # >= 2^26 elements -> 64 KB tiles with 256-bit loads; ragged tail
+    g = torch.Generator(device=DEV).manual_seed(77)
+    esz = torch.empty(0, dtype=dtype).element_size()
+    arena = (torch.randn(3 * n + 64, device=DEV, generator=g) * 2.0).to(dtype)
+    out = torch.zeros(3 * n + 64, dtype=torch.uint8, device=DEV)
+    offs = [0, n + 16 // esz + (16 // esz) * ((n // (16 // esz)) % 2), 2 * n + 48 // esz]   # 32-B aligned, 16-B only, 16-B only
+    offs[1] = ((n * esz + 31) // 32 * 32 + 16) // esz        # exactly 16 mod 32 bytes
+    offs[2] = ((2 * n * esz + 64 + 31) // 32 * 32) // esz    # 32-B aligned again, but its fp8 side is offset by the same elements
+    for o_ in offs:
+        rc = L.fp8b_encode(arena.data_ptr() + esz * o_, dt_code(dtype), out.data_ptr() + o_, n, None, stream_ptr())
+        assert rc == 0
+    import os
+    os.environ["FP8B_CAST_SHAPE"] = "1"                     # reference: always the small 16-byte tiles
+    try:
+        ref = torch.zeros_like(out)
+        for o_ in offs:
+            assert L.fp8b_encode(arena.data_ptr() + esz * o_, dt_code(dtype), ref.data_ptr() + o_, n, None, stream_ptr()) == 0
+    finally:
+        del os.environ["FP8B_CAST_SHAPE"]
+    assert torch.equal(out, ref)
+    samp = slice(offs[1], offs[1] + 50001)
+    x = arena[samp].cpu()
+    want = _oracle_encode(x) if dtype == torch.bfloat16 else c_oracle.encode(x.numpy())
+    assert np.array_equal(out[samp].cpu().numpy(), want)
+    batched = torch.zeros_like(out)
+    spans = make_spans([(arena.data_ptr() + esz * o_, batched.data_ptr() + o_, n) for o_ in offs])
+    assert L.fp8b_encode_batch(spans, 3, dt_code(dtype), stream_ptr()) == 0
+    assert torch.equal(batched, ref)
