@@ -47,6 +47,32 @@ __global__ void __launch_bounds__(256) read_slab_kernel(const uint4* __restrict_
     if (acc == 0x12345678u) *out = acc;
 }
 
+// 256-bit loads (sm_100 LDG.E.256): slab per CTA, U x 32 bytes in flight per thread
+template <int U, int T>
+__global__ void __launch_bounds__(T) read256_kernel(const uint4* __restrict__ in, size_t nvec16, unsigned* out)
+{
+    const size_t nvec = nvec16 / 2;
+    size_t per = (nvec + gridDim.x - 1) / gridDim.x;
+    size_t b = (size_t)blockIdx.x * per, e = b + per < nvec ? b + per : nvec;
+    unsigned acc = 0;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(in);
+    for (size_t v0 = b + threadIdx.x; v0 < e; v0 += (size_t)T * U) {
+        unsigned w[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            size_t v = v0 + (size_t)u * T;
+            if (v < e) asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                    : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7]) : "l"(base + v * 32));
+            else { for (int j = 0; j < 8; ++j) w[u][j] = 0; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += w[u][j];
+    }
+    if (acc == 0x12345678u) *out = acc;
+}
+
 template <int U>
 __global__ void __launch_bounds__(256) copy_kernel(const uint4* __restrict__ in, uint4* __restrict__ outp, size_t nvec)
 {
@@ -97,6 +123,19 @@ int main()
         rd("read slab U8", read_slab_kernel<8>, 148 * 4, bytes);
         rd("read slab U8", read_slab_kernel<8>, 512, bytes);
         rd("read slab U4", read_slab_kernel<4>, 4096, bytes);
+        auto rd256 = [&](const char* name, auto kernel, int grid, int threads) {
+            size_t nvec = bytes / 16;
+            float us = time_us([&](int i) {
+                const uint4* p = (const uint4*)(a + (bytes == small ? (size_t)(i % nrot) * small : 0));
+                kernel<<<grid, threads>>>(p, nvec, out); }, bytes == small ? 64 : 10);
+            printf("%-34s grid %5d  %8.1f MB  %8.2f us  %7.1f GB/s\n", name, grid, bytes / 1e6, us, bytes / us / 1e3);
+        };
+        rd256("read256 U4 T256", read256_kernel<4, 256>, 512, 256);
+        rd256("read256 U4 T256", read256_kernel<4, 256>, 148 * 4, 256);
+        rd256("read256 U2 T256", read256_kernel<2, 256>, 148 * 4, 256);
+        rd256("read256 U4 T512", read256_kernel<4, 512>, 148 * 2, 512);
+        rd256("read256 U4 T512", read256_kernel<4, 512>, 148, 512);
+        rd256("read256 U8 T256", read256_kernel<8, 256>, 148 * 2, 256);
     }
     for (size_t bytes : {small, big}) {
         size_t nvec = bytes / 16;
