@@ -728,6 +728,7 @@ def main():
                     "allgather_rank_major": lambda: lin(a, inv_a, torch.bfloat16, layout="rank_major"),
                     "allgather_row_major": lambda: lin(a, inv_a, torch.bfloat16, layout="row_major"),
                     "multicast_fused": lambda: lin(a, inv_a, torch.bfloat16, mode="multicast"),
+                    "peer_store_fused": lambda: lin(a, inv_a, torch.bfloat16, mode="peers"),
                 }
                 comp_us = max_over_ranks(torch, dist, res["us_per_call"])
                 sh = {"world": n_gpus, "compute_only_us_max_rank": round(comp_us, 2),
@@ -753,6 +754,8 @@ def main():
                         sh[name] = {"error": repr(e)[:200]}
                 sh["layouts"] = {"allgather_rank_major": "[world, M, N/world], no re-layout pass",
                                  "allgather_row_major": "(M, N) contiguous, one extra device pass",
+                                 "peer_store_fused": "(M, N) row-major on every rank, written by the GEMM epilogue with plain "
+                                                     "stores into every rank's symmetric buffer (own shard stays local)",
                                  "multicast_fused": "(M, N) row-major on every rank, written by the GEMM epilogue through "
                                                     "the NVSwitch multicast mapping; double-buffered, one symmetric-memory barrier per call"}
                 sub[key]["sharded"] = sh

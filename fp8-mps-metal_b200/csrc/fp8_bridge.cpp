@@ -359,6 +359,41 @@ void fp8_scaled_mm_multicast(torch::Tensor A, torch::Tensor B, torch::Tensor sca
     check_status(rc, "fp8b_scaled_mm_multicast");
 }
 
+// N-sharded linear with peer stores: `out` is this rank's full (M, full_N) symmetric buffer, `peer_deltas` a device
+// int64[world] tensor of byte offsets from it to every rank's buffer (0 for this rank).
+void fp8_scaled_mm_peers(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
+                         c10::optional<torch::Tensor> bias, torch::Tensor out, torch::Tensor peer_deltas, int64_t n0)
+{
+    TORCH_CHECK(A.dtype() == torch::kUInt8 && B.dtype() == torch::kUInt8, "A and B must be uint8 (FP8 encoded)");
+    TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous CUDA tensors");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "K dimension mismatch between A and B");
+    TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.is_contiguous() && out.size(0) == A.size(0), "out must be (M, full_N) contiguous");
+    TORCH_CHECK(peer_deltas.is_cuda() && peer_deltas.scalar_type() == at::kLong && peer_deltas.is_contiguous(),
+                "peer_deltas must be a contiguous CUDA int64 tensor");
+    const int64_t M = A.size(0), K = A.size(1), N = B.size(0), full_N = out.size(1);
+    TORCH_CHECK(n0 >= 0 && n0 + N <= full_N, "column block outside the full matrix");
+    c10::cuda::CUDAGuard guard(A.device());
+    torch::Tensor sa = as_device_f32(scale_a, A.device());
+    torch::Tensor sb = as_device_f32(scale_b, A.device());
+    torch::Tensor bias_t;
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = bias->to(A.device()).contiguous().reshape({-1});
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    const int odt = to_fp8b_dtype(out.scalar_type());
+    void* c_local = static_cast<uint8_t*>(out.data_ptr()) + n0 * out.element_size();
+    int rc = fp8b_scaled_mm_peers(u8_ptr(A), u8_ptr(B), c_local, peer_deltas.data_ptr<int64_t>(), (int)peer_deltas.numel(), odt,
+                                  (int)M, (int)N, (int)K, full_N, sa.data_ptr<float>(), (int)sa.numel(),
+                                  sb.data_ptr<float>(), (int)sb.numel(), bias_ptr, bias_dt, nullptr, current_stream());
+    check_status(rc, "fp8b_scaled_mm_peers");
+}
+
 // per-row fp8_quantize of a 2-D tensor: returns (uint8 (rows, cols), inv_scale float32 [rows])
 std::tuple<torch::Tensor, torch::Tensor> fp8_quantize_rowwise(torch::Tensor input)
 {
@@ -461,6 +496,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           "FP8 scaled matmul storing through an NVSwitch multicast address (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out_dtype"),
           py::arg("mc_ptr"), py::arg("full_N"), py::arg("n0"));
+    m.def("fp8_scaled_mm_peers", &fp8_scaled_mm_peers,
+          "FP8 scaled matmul storing its tiles into every rank's symmetric buffer with peer stores (N-sharded linear)",
+          py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out"),
+          py::arg("peer_deltas"), py::arg("n0"));
     m.def("select_algo", &select_algo, py::arg("A"), py::arg("B"), py::arg("out_dtype"));
     m.def("launch_count", []() { return (uint64_t)fp8b_launch_count(); });
     m.def("set_option", [](int option, int value) { check_status(fp8b_set_option(option, value), "fp8b_set_option"); });

@@ -239,3 +239,25 @@ extern "C" int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B,
     if (plan == 2) return FP8B_ERR_INVALID;
     return launch_gemv_fhfma(a, make_epi(a), X, x_dtype, inv_scale_a_out);
 }
+
+extern "C" int fp8b_scaled_mm_peers(const uint8_t* A, const uint8_t* B, void* C_local, const int64_t* peer_deltas, int world,
+                                    int out_dtype, int M, int N, int K, int64_t ldc,
+                                    const float* scale_a, int scale_a_len,
+                                    const float* scale_b, int scale_b_len,
+                                    const void* bias, int bias_dtype,
+                                    const float* scale_result, void* stream)
+{
+    if (world < 2 || world > 8 || !peer_deltas) return FP8B_ERR_INVALID;
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C_local; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = const_cast<int64_t*>(peer_deltas); a.ws_bytes = (size_t)world * sizeof(int64_t); a.st = (cudaStream_t)stream;
+    a.store_mc = 2 | (world << 8);
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (M == 0 || N == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    return launch_gemm_tcgen05(a);
+}

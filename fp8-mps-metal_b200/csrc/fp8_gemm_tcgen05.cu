@@ -275,13 +275,18 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 
 // ------------------------------------------------------------------------------ kernel
 
-template <int BN, int CG>
+// PEERS: the epilogue stores every 16-byte piece once per GPU of an N-sharded linear -- into this rank's buffer and,
+// as plain st.global over NVLink, into the peers' symmetric buffers (byte deltas from the local address in a small
+// device table, GemmParams::dbg).  Unlike the multicast mode, a rank's own shard does not travel through the
+// switch and back.  A separate instantiation, so the single-GPU and multicast kernels are untouched.
+template <int BN, int CG, bool PEERS = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
                         const GemmParams p)
 {
     using Cfg = GemmCfg<BN, CG>;
+    long long* const dbg = PEERS ? nullptr : p.dbg;  // (PEERS: the field carries the peer delta table instead)
     constexpr int kTileM = kBM * CG;                 // rows of C per tile (per CTA pair when CG == 2)
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool is_leader = cta_rank == 0;
@@ -377,10 +382,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
-                const long long t_m0 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
+                const long long t_m0 = (dbg && blockIdx.x == 0) ? clock64() : 0;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);           // epilogue has drained this accumulator
                 tc_fence_after();
-                const long long t_m1 = (p.dbg && blockIdx.x == 0) ? clock64() : 0;
+                const long long t_m1 = (dbg && blockIdx.x == 0) ? clock64() : 0;
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 const uint32_t idesc_t = ((tile < p.full_tiles) ? idesc : make_idesc(kTileM, BN / 2)) | idesc_fmt;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -402,9 +407,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 if (elected) {
                     if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
-                    if (p.dbg && blockIdx.x == 0) {
+                    if (dbg && blockIdx.x == 0) {
                         const int ti = (tile - worker) / num_workers;
-                        if (ti < 64) { p.dbg[ti * 8 + 0] = t_m0; p.dbg[ti * 8 + 1] = t_m1; p.dbg[ti * 8 + 2] = clock64(); p.dbg[ti * 8 + 3] = 0; }
+                        if (ti < 64) { dbg[ti * 8 + 0] = t_m0; dbg[ti * 8 + 1] = t_m1; dbg[ti * 8 + 2] = clock64(); dbg[ti * 8 + 3] = 0; }
                     }
                 }
                 __syncwarp();
@@ -420,6 +425,21 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const Epi& e = p.epi;
         const float sr = e.sr ? *e.sr : 1.0f;
         const float sb0 = e.sb[0];
+        long long peer_delta[8];                     // PEERS: byte offset of every rank's buffer from the local one (0 = self)
+        const int peer_world = PEERS ? (p.store_mc >> 8) : 0;
+        if (PEERS) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) peer_delta[r] = r < peer_world ? p.dbg[r] : 0;
+        }
+        auto store16 = [&](void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+            if (PEERS) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < peer_world) stg_v4(reinterpret_cast<uint8_t*>(ptr) + peer_delta[r], a, b, c, d, 0);
+            } else {
+                stg_v4(ptr, a, b, c, d, p.store_mc);
+            }
+        };
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = worker; tile < num_tiles; tile += num_workers) {
             const TileCoord tc = decode_tile(p, tile, BN);
@@ -429,10 +449,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
             const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
-            const long long t_e0 = (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+            const long long t_e0 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const long long t_e1 = (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+            const long long t_e1 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = col_part * cols_per_warp; c0 < (col_part + 1) * cols_per_warp; c0 += 32) {
@@ -568,7 +588,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                 const int gm = m_idx + q * 32 + rr;
                                 uint32_t a0, a1, a2, a3;
                                 lds_v4(wbase + (uint32_t)rr * row_bytes + (uint32_t)((piece ^ (rr & (ppr - 1))) * 16), a0, a1, a2, a3);
-                                if (gm < p.M) stg_v4(cbase + (size_t)gm * e.ldc * esz, a0, a1, a2, a3, p.store_mc);
+                                if (gm < p.M) store16(cbase + (size_t)gm * e.ldc * esz, a0, a1, a2, a3);
                             }
                             __syncwarp();
                         }
@@ -576,7 +596,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         uint8_t* dst = reinterpret_cast<uint8_t*>(e.C) + ((size_t)m * e.ldc + n0) * (is_f32 ? 4 : 2);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (j < ppc) stg_v4(dst + 16 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3], p.store_mc);
+                            if (j < ppc) store16(dst + 16 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                     }
                 } else if (m_ok) {
                     // edge chunk / unaligned output: scalar, bounds-checked
@@ -587,9 +607,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
             }
-            if (p.dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) {
+            if (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) {
                 const int ti = (tile - worker) / num_workers;
-                if (ti < 64) { p.dbg[ti * 8 + 4] = t_e0; p.dbg[ti * 8 + 5] = t_e1; p.dbg[ti * 8 + 6] = clock64(); }
+                if (ti < 64) { dbg[ti * 8 + 4] = t_e0; dbg[ti * 8 + 5] = t_e1; dbg[ti * 8 + 6] = clock64(); }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -645,12 +665,12 @@ bool tcgen05_supported(const MMArgs& a)
     return a.M >= 1 && a.N >= 1 && a.K >= 16 && (a.K % 16 == 0) && aligned(a.A, 16) && aligned(a.B, 16);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool PEERS = false>
 static int launch_tcgen05_cfg(const MMArgs& a)
 {
     using Cfg = GemmCfg<BN, CG>;
     static std::atomic<int> attr_done[64];
-    if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG>, Cfg::kSmemBytes, attr_done)) return rc;
+    if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG, PEERS>, Cfg::kSmemBytes, attr_done)) return rc;
 
     CUtensorMap tmap_a, tmap_b;
     if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;
@@ -681,6 +701,10 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.debug = (tune_int("FP8B_GEMM_DEBUG", 0) & 0xFF) | (a.a_fmt ? 0x100 : 0) | (a.b_fmt ? 0x200 : 0);
     p.store_mc = a.store_mc;
     p.dbg = nullptr;
+    if (PEERS) {                             // store_mc = 2 | world << 8; a.ws = device table of world byte deltas
+        p.dbg = static_cast<long long*>(a.ws);
+        p.debug &= ~16;
+    }
     if (p.debug & 16) {                      // profiling only: allocates and synchronises
         static long long* dbuf = nullptr;
         if (!dbuf) cudaMalloc(&dbuf, 64 * 8 * sizeof(long long));
@@ -688,6 +712,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
         p.dbg = dbuf;
     }
     // multimem.st has no sub-word form: the multicast mode needs every chunk on the 16-byte path
+    // multimem.st / peer stores have no sub-word form: both modes need every chunk on the 16-byte path
     if (a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
     const int tiles = p.num_work;
@@ -710,9 +735,9 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     // changed nothing: 104.17 vs 104.12 us back to back.  The kernel is power-limited, idle gaps only buy clock.)
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG>, tmap_a, tmap_b, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG, PEERS>, tmap_a, tmap_b, p);
     if (e != cudaSuccess) return cuda_fail(e);
-    if (p.dbg) {
+    if (!PEERS && p.dbg) {
         long long h[64 * 8];
         cudaDeviceSynchronize();
         cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
@@ -751,6 +776,15 @@ int launch_gemm_tcgen05(const MMArgs& a)
         } else {
             const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
             cfg = (a.N > 128 && t_256 >= 2L * sms) ? 1 : 2;
+        }
+    }
+    if ((a.store_mc & 0xFF) == 2) {          // peer stores (N-sharded linear): the CTA-pair configurations only
+        if ((a.store_mc >> 8) < 2 || (a.store_mc >> 8) > 8 || !a.ws) return FP8B_ERR_INVALID;
+        switch (cfg) {
+            case 3: return launch_tcgen05_cfg<256, 2, true>(a);
+            case 4: return launch_tcgen05_cfg<128, 2, true>(a);
+            case 5: return launch_tcgen05_cfg<192, 2, true>(a);
+            default: return FP8B_ERR_UNSUPPORTED;
         }
     }
     switch (cfg) {

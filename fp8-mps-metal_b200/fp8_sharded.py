@@ -11,6 +11,9 @@ shard -- no reduction is needed -- and ONE exchange step assembles the (M,N) res
                     [w, M, N/w] buffer, exposed either as is (layout="rank_major", zero extra
                     passes) or re-laid to the row-major (M,N) tensor stock _scaled_mm returns
                     (layout="row_major", one extra device pass);
+  mode="peers"      fused, unicast: the epilogue stores each tile into this rank's result and, with plain
+                    stores over NVLink, into the same place of every peer's result (symmetric memory).
+                    Each GPU receives (w-1)/w of the output; no NVLS needed.
   mode="multicast"  fused: the GEMM epilogue writes each output tile straight into the row-major
                     (M,N) result of EVERY rank through an NVSwitch multicast mapping
                     (multimem.st), so the exchange overlaps the math tile by tile and no gather or
@@ -94,6 +97,8 @@ class ShardedScaledMM:
             mode = self.best_mode() if layout == "row_major" else "allgather"
         if mode == "multicast":
             return self.forward_multicast(x_u8, scale_a, out_dtype)
+        if mode == "peers":
+            return self.forward_peers(x_u8, scale_a, out_dtype)
         M = x_u8.shape[0]
         odt = out_dtype or torch.float32
         if self.world == 1:
@@ -152,7 +157,47 @@ class ShardedScaledMM:
         hdl.barrier(channel=0)                                  # every rank's tiles have landed everywhere
         return buf
 
+    def forward_peers(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """Like forward_multicast, with peer stores: the GEMM epilogue writes every tile into this rank's buffer and
+        into each peer's buffer (unicast over NVLink).  A rank's own shard never leaves the GPU, so the NVLink
+        ingress per GPU is (w-1)/w of the output instead of all of it.  Same double-buffering and single barrier."""
+        import fp8_mps_native
+        M = x_u8.shape[0]
+        odt = out_dtype or torch.float32
+        if self.world == 1:
+            return self.local(x_u8, scale_a, out_dtype)
+        key, pair, turn = self._symm_buffers(M, odt, x_u8.device)
+        buf, hdl = pair[turn]
+        self._symm = (key, pair, turn ^ 1)
+        deltas = self._peer_deltas(turn, buf, hdl)
+        if self.n1 > self.n0:
+            try:
+                fp8_mps_native._get_lib().fp8_scaled_mm_peers(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
+                                                              deltas, int(self.n0))
+            except RuntimeError as e:
+                if "unsupported" not in str(e):
+                    raise
+                raise RuntimeError("peer-store mode needs M > 128, N/world > 128 and 16-byte aligned shards: " + str(e))
+        hdl.barrier(channel=0)                                  # every rank's tiles have landed everywhere
+        return buf
+
+    def _peer_deltas(self, turn, buf, hdl):
+        cache = getattr(self, "_deltas", None)
+        if cache is None or cache[0] is not self._symm[1]:
+            cache = (self._symm[1], {})
+            self._deltas = cache
+        if turn not in cache[1]:
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            assert len(ptrs) == self.world
+            local = ptrs[self.rank]
+            cache[1][turn] = torch.tensor([p - local for p in ptrs], dtype=torch.int64, device=buf.device)
+        return cache[1][turn]
+
     def best_mode(self) -> str:
-        """Measured on 8 x B200 (C4, bf16 out, row-major result on every rank): the fused multicast path beats
-        GEMM + NCCL all-gather at every world size (w=8: 166 us vs 207 us rank-major / 324 us row-major)."""
-        return "multicast" if self.world > 1 else "allgather"
+        """Measured on 8 x B200 (C4, bf16 out, row-major result on every rank; profiles/r1_scaling.md): both fused
+        paths beat GEMM + NCCL all-gather at every world size.  Peer stores win while few peers have to be written
+        (w=2: 122 us vs 179 us multicast vs 202 us all-gather; w=4: 151 / 168 / 191), the multicast mapping wins
+        at w=8 (165 us vs 169 us peers vs 199 us)."""
+        if self.world <= 1:
+            return "allgather"
+        return "peers" if self.world <= 4 else "multicast"

@@ -263,6 +263,23 @@ FP8B_API int fp8b_scaled_mm_multicast(const uint8_t* A, const uint8_t* B, void* 
                              const void* bias, int bias_dtype,
                              const float* scale_result, void* stream);
 
+/*
+ * The same N-sharded linear with PEER STORES instead of the multicast mapping: the epilogue writes every 16-byte
+ * piece of the output tile into this rank's (M,N) buffer and, as plain stores over NVLink, into the same offset of
+ * each peer's buffer.  peer_deltas: DEVICE array of `world` (2..8) byte offsets, delta[r] = (address of rank r's
+ * buffer as mapped in this process) - (address of the local buffer); the entry of the calling rank is 0.
+ * C_local points at this rank's shard column inside its own buffer (ldc = full N).  Against the multicast mode a
+ * rank's own shard does not travel to the switch and back, so each GPU receives (world-1)/world of the output
+ * instead of all of it: the better plan for small worlds.  Same 16-byte-path requirements as the multicast mode;
+ * CTA-pair tile configurations only (M > 128 and N > 128), else FP8B_ERR_UNSUPPORTED.
+ */
+FP8B_API int fp8b_scaled_mm_peers(const uint8_t* A, const uint8_t* B, void* C_local, const int64_t* peer_deltas, int world,
+                         int out_dtype, int M, int N, int K, int64_t ldc,
+                         const float* scale_a, int scale_a_len,
+                         const float* scale_b, int scale_b_len,
+                         const void* bias, int bias_dtype,
+                         const float* scale_result, void* stream);
+
 /* The algorithm FP8B_MM_AUTO resolves to for this problem (pointers supply the alignment). */
 FP8B_API int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const void* C, int out_dtype,
                           int M, int N, int K, int64_t ldc);

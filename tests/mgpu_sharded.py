@@ -5,7 +5,7 @@
         tests/mgpu_sharded.py
 
 Every rank compares (a) the NCCL all-gather path, row-major and rank-major layouts, and (b) the fused
-multicast-store path against the un-sharded GEMM it computes locally with the same kernel, and a slab of
+multicast-store and peer-store paths against the un-sharded GEMM it computes locally with the same kernel, and a slab of
 the result against the CPU oracle.  Prints one PASS/FAIL line per rank; exit code 0 only if all pass."""
 import os
 import sys
@@ -62,6 +62,20 @@ def main():
                 ok = ok and mc_ok
             except Exception as e:   # NVLS unavailable is reported, not hidden
                 mc_state = f"unavailable: {type(e).__name__}: {str(e)[:120]}"
+        pe_state = "skipped"
+        if N % (32 * world) == 0 and lin.width == N // world and M > 128 and N // world > 128:
+            try:
+                ype = lin(Ad, sad, out_dtype=torch.bfloat16, mode="peers")
+                torch.cuda.synchronize()
+                pe_ok = bool(torch.equal(ype, full))
+                ype2 = lin(Ad, sad, out_dtype=torch.bfloat16, mode="peers")          # buffer reuse
+                torch.cuda.synchronize()
+                pe_ok = pe_ok and bool(torch.equal(ype2, full))
+                pe_state = "ok" if pe_ok else "MISMATCH"
+                ok = ok and pe_ok
+            except Exception as e:
+                pe_state = f"FAILED: {type(e).__name__}: {str(e)[:160]}"
+                ok = False
         rows = slice(0, min(M, 128))
         ref = o.scaled_mm(A[rows].numpy(), W.numpy(), sa.numpy(), sb.numpy(),
                           None if bias is None else bias.float().numpy(), None, "bf16", accum="f32")
@@ -69,7 +83,7 @@ def main():
         case_ok = same and same_rank and err <= 3e-3
         ok = ok and case_ok
         msgs.append(f"M{M} K{K} N{N}: allgather={'ok' if same else 'MISMATCH'} rank_major={'ok' if same_rank else 'MISMATCH'} "
-                    f"multicast={mc_state} oracle_rel_rmse={err:.2e}")
+                    f"multicast={mc_state} peers={pe_state} oracle_rel_rmse={err:.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     for m in msgs:
