@@ -4,11 +4,15 @@
 // Reference: fp8_to_half_kernel (fp8_matmul.metal:215-223) and float_to_fp8_kernel (:228-236), one
 // element per thread, with the scale / up-conversion / pre-scale done as separate torch passes
 // on the host side (fp8_mps_native.py:121-122, :142, :170-179).  Here each is ONE pass over HBM:
-// every thread-iteration moves exactly one 16-byte vector on the wide side (the f16/bf16/f32 side)
-// and the matching 4/8-byte vector on the FP8 side, so both sides are fully coalesced
-// (a warp touches 512 contiguous bytes wide-side, 128/256 contiguous bytes FP8-side); UNROLL
-// independent vectors are in flight per thread.  HBM-bound: 3 B/element (16-bit side) or
-// 5 B/element (f32 side) of algorithmic traffic.
+// every thread-iteration moves one 16- (or 32-) byte vector on the wide side (the f16/bf16/f32 side)
+// and the matching vector on the FP8 side, so both sides are fully coalesced; the work is cut into
+// tiles of THREADS x UNROLL vectors (see "Tiles" below for the measured launch shapes).  HBM-bound:
+// 3 B/element (16-bit side) or 5 B/element (f32 side) of algorithmic traffic.
+//
+// In this file: tile kernels (single tensor), batched kernels (many tensors, one launch, span table in
+// the kernel parameters), the amax / finalize kernels of fp8_quantize, the row-wise quantise kernels
+// (two-pass and register-resident), float8_e5m2 decode (FMT template parameter), and the C entry points.
+// The tile kernels run under programmatic dependent launch: coherent loads only.
 #include "fp8_codec.cuh"
 #include "fp8_common.cuh"
 

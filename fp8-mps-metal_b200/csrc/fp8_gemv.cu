@@ -6,8 +6,9 @@
 //
 // HBM-bound: the weight matrix B (N*K bytes) is streamed exactly once.
 //   * one warp per weight row, 8 rows per CTA; each lane issues UNROLL independent 16-byte
-//     ld.global.nc.L1::no_allocate loads (512 contiguous bytes per warp per load) before
-//     consuming any of them;
+//     ld.global.L1::no_allocate loads (512 contiguous bytes per warp per load) before consuming any
+//     of them.  Coherent loads, not .nc: every launch uses programmatic dependent launch and ptxas
+//     moves non-coherent loads above griddepcontrol.wait (see ld_x_v4 / ldg_w_v4);
 //   * x (the A rows) is decoded once per CTA into shared memory as fp16 (every e4m3 value is
 //     exact in fp16), split in two 16-byte planes so the per-lane LDS.128 are conflict-free;
 //   * weights are decoded in registers with cvt.rn.f16x2.e4m3x2 (2 elements / instruction) and
@@ -19,6 +20,8 @@
 //     (1 x S x 1) and the S partial sums are reduced through distributed shared memory by the
 //     rank-0 CTA, in rank order (deterministic, no workspace, no atomics);
 //   * scales, bias, scale_result and the output cast are fused into the epilogue.
+//   * fp8_gemv_xq_kernel: the same kernel fed with UN-quantised activations (fused per-row
+//     fp8_quantize, fp8b_linear_dynamic without a workspace);
 //   * NaN bytes: the hardware decode yields NaN where the reference decodes 0 (metal:21).  A NaN
 //     accumulator can only come from such a byte, so it is detected after the reduction and that
 //     output alone is recomputed with the masked scalar loop.
