@@ -66,6 +66,13 @@ def decode_table() -> np.ndarray:
     return np.array([L.fp8o_decode(b) for b in range(256)], dtype=np.float32)
 
 
+def decode_table_e5m2() -> np.ndarray:
+    L = lib()
+    L.fp8o_decode_e5m2.restype = ctypes.c_float
+    L.fp8o_decode_e5m2.argtypes = [ctypes.c_uint8]
+    return np.array([L.fp8o_decode_e5m2(b) for b in range(256)], dtype=np.float32)
+
+
 def encode(x: np.ndarray) -> np.ndarray:
     """x: float32, float16, or uint16 holding bf16 bits (pass kind='bf16')."""
     x = np.ascontiguousarray(x)

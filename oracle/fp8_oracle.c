@@ -8,6 +8,7 @@
  * loop for loop, with the same fp32 arithmetic and summation order as the shader:
  *
  *   fp8o_decode        fp8_matmul.metal:19-40
+ *   fp8o_decode_e5m2   (no reference counterpart: the e5m2 format's definition, see below)
  *   fp8o_encode        fp8_matmul.metal:44-92   (floor(log2 v) taken exactly, like the
  *                                                reference's test_fp8_correctness.py:84)
  *   fp8o_to_half       fp8_matmul.metal:215-223 + fp8_mps_native.py:121-122
@@ -91,6 +92,19 @@ float fp8o_decode(uint8_t bits)
         value = mantissa * ldexpf(1.0f, exponent);          /* :36 exp2 */
     }
     return sign ? -value : value;                           /* :39 */
+}
+
+/* float8_e5m2: not a reference codec (the reference mis-routes e5m2 tensors into fp8o_decode's format).
+ * The format's own definition, arithmetic form: sign(1) exponent(5, bias 15) mantissa(2), IEEE inf / NaN at
+ * exponent 31.  Pinned against PyTorch's CPU cast by tests/test_oracle_golden.py. */
+float fp8o_decode_e5m2(uint8_t bits)
+{
+    unsigned sign = (bits >> 7) & 1, e = (bits >> 2) & 0x1F, m = bits & 0x3;
+    float value;
+    if (e == 31) value = m ? NAN : INFINITY;
+    else if (e == 0) value = (float)m / 4.0f * ldexpf(1.0f, -14);
+    else value = (1.0f + (float)m / 4.0f) * ldexpf(1.0f, (int)e - 15);
+    return sign ? -value : value;
 }
 
 static void ensure_lut(void)

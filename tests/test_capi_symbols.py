@@ -87,3 +87,31 @@ def test_bridge_errors_are_python_exceptions():
         fp8_metal.fp8_dequantize(torch.zeros(4, dtype=torch.uint8), torch.ones(1))
     with pytest.raises(RuntimeError, match="uint8"):
         fp8_metal.fp8_dequantize(torch.zeros(4, dtype=torch.int32), torch.ones(1))
+
+
+def test_ctypes_bindings_match_the_header_prototypes():
+    """Guards the drop-in boundary against drift: for every prototype in include/fp8_b200.h the binding the tests
+    (and INTEGRATION.md's example) use must pass the same number of arguments, with pointer / integer kinds in
+    the same positions."""
+    import ctypes
+    import re
+    from _util import HEADER
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    L = capi()
+    checked = 0
+    for m in re.finditer(r"FP8B_API\s+[\w\s\*]+?\b(fp8b_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        plist = [] if params in ("void", "") else [p.strip() for p in params.split(",")]
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            assert not plist or name in ("fp8b_scaled_mm_multicast", "fp8b_scaled_mm_peers"), f"{name}: no argtypes set"
+            continue
+        assert len(fn.argtypes) == len(plist), f"{name}: header has {len(plist)} parameters, binding {len(fn.argtypes)}"
+        for decl, ct in zip(plist, fn.argtypes):
+            is_ptr = "*" in decl
+            assert is_ptr == (ct is ctypes.c_void_p or ct is ctypes.c_char_p), f"{name}: '{decl}' bound as {ct}"
+            if not is_ptr:
+                want = ctypes.c_size_t if "size_t" in decl else ctypes.c_int64 if "int64_t" in decl else ctypes.c_int
+                assert ct is want, f"{name}: '{decl}' bound as {ct}"
+        checked += 1
+    assert checked >= 18

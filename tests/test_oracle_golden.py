@@ -165,6 +165,8 @@ def test_e5m2_decode_table_matches_torch_cast():
     assert nan.sum() == 6 and np.array_equal(np.isnan(ours), nan)
     assert np.array_equal(ours[~nan].view(np.uint32), ref[~nan].view(np.uint32))
     assert ours[0x7C] == np.inf and ours[0xFC] == -np.inf and ours[0x7B] == 57344.0 and ours[0x01] == 2.0 ** -16
+    c_tab = c_oracle.decode_table_e5m2()                     # the plain-C restatement (arithmetic, not a bit shift)
+    assert np.array_equal(np.isnan(c_tab), nan) and np.array_equal(c_tab[~nan].view(np.uint32), ref[~nan].view(np.uint32))
     # every value is exactly representable in fp16 and bf16
     assert np.array_equal(g["decode_f16_bits"][~nan], (np.arange(256, dtype=np.uint16) << 8)[~nan])
     assert np.array_equal(o.f32_to_bf16_bits(ours[~nan]), g["decode_bf16_bits"][~nan])
