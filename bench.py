@@ -270,8 +270,9 @@ def run_reference(args):
     fn = (lambda: c_oracle.scaled_mm(x, W, sa, sb)) if use_c else \
         (lambda: o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"))
     calls_per_step = 2                          # bounded sample of the 128-call step
-    for _ in range(max(args.warmup, 1)):
-        fn()
+    for _ in range(max(args.warmup, 3)):         # W >= 3 warm-up steps, like the GPU arm
+        for _ in range(calls_per_step):
+            fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _ in range(calls_per_step):
