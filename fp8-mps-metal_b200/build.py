@@ -27,7 +27,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libfp8_b200.so")
 
-CU_SOURCES = ["fp8_cast.cu", "fp8_gemv.cu", "fp8_gemv_mma.cu", "fp8_gemv_rows.cu", "fp8_gemm_simt.cu", "fp8_gemm_tcgen05.cu", "fp8_capi.cu"]
+CU_SOURCES = ["fp8_cast.cu", "fp8_gemv.cu", "fp8_gemv_mma.cu", "fp8_gemv_rows.cu", "fp8_gemv_batch.cu", "fp8_gemm_simt.cu", "fp8_gemm_tcgen05.cu", "fp8_capi.cu"]
 HEADERS = ["fp8_codec.cuh", "fp8_common.cuh", "fp8_mm.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -359,6 +359,59 @@ void fp8_scaled_mm_multicast(torch::Tensor A, torch::Tensor B, torch::Tensor sca
     check_status(rc, "fp8b_scaled_mm_multicast");
 }
 
+// Several independent M = 1 GEMVs (same K, same out dtype) in one launch: fp8b_gemv_batch.
+std::vector<torch::Tensor> fp8_scaled_mm_many(std::vector<torch::Tensor> xs, std::vector<torch::Tensor> Ws,
+                                              std::vector<torch::Tensor> scale_xs, std::vector<torch::Tensor> scale_ws,
+                                              c10::optional<std::vector<torch::Tensor>> biases,
+                                              c10::optional<at::ScalarType> out_dtype)
+{
+    const size_t n = Ws.size();
+    TORCH_CHECK(xs.size() == n && scale_xs.size() == n && scale_ws.size() == n, "xs, Ws and the scale lists must have equal length");
+    TORCH_CHECK(!biases.has_value() || biases->size() == n, "biases must have one entry per problem");
+    std::vector<torch::Tensor> outs(n);
+    if (n == 0) return outs;
+    const auto dev = Ws[0].device();
+    TORCH_CHECK(dev.is_cuda(), "operands must be CUDA tensors");
+    c10::cuda::CUDAGuard guard(dev);
+    const at::ScalarType odt = out_dtype.value_or(at::kFloat);
+    const int64_t K = Ws[0].size(1);
+    std::vector<torch::Tensor> keep;                              // converted scales / biases stay alive until the launch
+    std::vector<fp8b_gemv_item> items(n);
+    int bias_dt = FP8B_F32;
+    bool bias_seen = false;
+    for (size_t i = 0; i < n; ++i) {
+        const torch::Tensor& x = xs[i];
+        const torch::Tensor& W = Ws[i];
+        TORCH_CHECK(x.dtype() == torch::kUInt8 && W.dtype() == torch::kUInt8, "x and W must be uint8 (FP8 encoded)");
+        TORCH_CHECK(x.device() == dev && W.device() == dev, "all operands must be on one device");
+        TORCH_CHECK(x.is_contiguous() && W.is_contiguous(), "x and W must be contiguous");
+        TORCH_CHECK(W.dim() == 2 && W.size(1) == K && x.numel() == K, "every problem must have M = 1 and the same K");
+        const int64_t N = W.size(0);
+        torch::Tensor sx = as_device_f32(scale_xs[i], dev), sw = as_device_f32(scale_ws[i], dev);
+        TORCH_CHECK(sx.numel() == 1, "scale_x must have 1 element");
+        TORCH_CHECK(sw.numel() == 1 || sw.numel() == N, "scale_w must have 1 or N elements");
+        keep.push_back(sx); keep.push_back(sw);
+        outs[i] = torch::empty({1, N}, torch::TensorOptions().dtype(odt).device(dev));
+        fp8b_gemv_item& q = items[i];
+        q.x = u8_ptr(x); q.W = u8_ptr(W); q.y = outs[i].data_ptr(); q.N = (int)N;
+        q.scale_x = sx.data_ptr<float>(); q.scale_w = sw.data_ptr<float>(); q.scale_w_len = (int)sw.numel();
+        q.bias = nullptr;
+        if (biases.has_value() && (*biases)[i].defined() && (*biases)[i].numel() > 0) {
+            torch::Tensor bt = (*biases)[i].to(dev).contiguous().reshape({-1});
+            if (bt.scalar_type() != at::kFloat && bt.scalar_type() != at::kHalf && bt.scalar_type() != at::kBFloat16)
+                bt = bt.to(torch::kFloat32);
+            TORCH_CHECK(bt.numel() == N, "bias must have N elements");
+            const int dt = to_fp8b_dtype(bt.scalar_type());
+            TORCH_CHECK(!bias_seen || dt == bias_dt, "all biases must share one dtype");
+            bias_dt = dt; bias_seen = true;
+            keep.push_back(bt);
+            q.bias = bt.data_ptr();
+        }
+    }
+    check_status(fp8b_gemv_batch(items.data(), (int)n, (int)K, to_fp8b_dtype(odt), bias_dt, current_stream()), "fp8b_gemv_batch");
+    return outs;
+}
+
 // N-sharded linear with peer stores: `out` is this rank's full (M, full_N) symmetric buffer, `peer_deltas` a device
 // int64[world] tensor of byte offsets from it to every rank's buffer (0 for this rank).
 void fp8_scaled_mm_peers(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
@@ -496,6 +549,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           "FP8 scaled matmul storing through an NVSwitch multicast address (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out_dtype"),
           py::arg("mc_ptr"), py::arg("full_N"), py::arg("n0"));
+    m.def("fp8_scaled_mm_many", &fp8_scaled_mm_many, "Several independent M = 1 FP8 GEMVs of one K in one launch",
+          py::arg("xs"), py::arg("Ws"), py::arg("scale_xs"), py::arg("scale_ws"), py::arg("biases") = py::none(),
+          py::arg("out_dtype") = py::none());
     m.def("fp8_scaled_mm_peers", &fp8_scaled_mm_peers,
           "FP8 scaled matmul storing its tiles into every rank's symmetric buffer with peer stores (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out"),

@@ -116,6 +116,19 @@ def scaled_mm_patch(input, other, scale_a=None, scale_b=None, bias=None, scale_r
     return _get_lib().scaled_mm_patch(input, other, scale_a, scale_b, bias, scale_result, out_dtype)
 
 
+def fp8_scaled_mm_many(xs, Ws, scale_xs, scale_ws, biases=None, out_dtype=None):
+    """Several independent decode GEMVs in ONE launch: ``[fp8_scaled_mm_fused(x, W, sx, sw, bias, None, out_dtype)
+    for ...]`` for M = 1 problems that share K (the Q/K/V or gate/up projections of a layer; the x may be the same
+    tensor).  A C2-sized GEMV spends a third of its time in launch ramp-up and drain; sharing the launch pays that
+    once.  xs: list of (1,K) uint8; Ws: list of (N_i,K) uint8; scale_xs: list of 1-element tensors; scale_ws: list of
+    1- or N_i-element tensors; biases: optional list (entries may be None).  Returns a list of (1,N_i) tensors."""
+    lib = _get_lib()
+    if biases is not None:
+        biases = [b if b is not None else torch.empty(0) for b in biases]
+    return lib.fp8_scaled_mm_many([_to_device(x) for x in xs], [_to_device(W) for W in Ws], list(scale_xs), list(scale_ws),
+                                  biases, out_dtype)
+
+
 def fp8_dequantize(input: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
     """
     FP8 -> half dequantization (reference: fp8_mps_native.py:98-124).

@@ -206,6 +206,27 @@ FP8B_API int fp8b_scaled_mm(const uint8_t* A, const uint8_t* B, void* C, int out
                    int algo, void* stream);
 
 /*
+ * Several independent M = 1 GEMVs in ONE launch (per 16 items):  y_i = _scaled_mm(x_i (1,K), W_i (N_i,K)^T) with
+ * per-tensor scale_x, per-tensor or per-row scale_w, optional bias, all of one K, one out_dtype and one bias_dtype.
+ * The reference issues one fp8_scaled_vecmat_kernel per projection (fp8_mps_native.py:78-86); on a B200 a third of a
+ * decode GEMV's time is launch ramp-up and drain, which the projections of a layer that are independent of each
+ * other (Q/K/V, gate/up; the x_i may be the same pointer) can pay once.  `items` is a HOST array; results are those
+ * of fp8b_scaled_mm's M = 1 kernel.  Needs K % 16 == 0, 16 <= K <= 49152 and 16-byte aligned x_i / W_i, else
+ * FP8B_ERR_UNSUPPORTED.  N_i == 0 items are skipped.
+ */
+typedef struct fp8b_gemv_item {
+    const uint8_t* x;          /* (K,)   e4m3fn bytes */
+    const uint8_t* W;          /* (N,K)  e4m3fn bytes, row-major */
+    void* y;                   /* (N,)   out_dtype */
+    int N;
+    const float* scale_x;      /* [1] */
+    const float* scale_w;      /* [1] or [N] */
+    int scale_w_len;
+    const void* bias;          /* [N] of bias_dtype, or NULL */
+} fp8b_gemv_item;
+FP8B_API int fp8b_gemv_batch(const fp8b_gemv_item* items, int count, int K, int out_dtype, int bias_dtype, void* stream);
+
+/*
  * fp8b_scaled_mm with per-operand formats.  e4m3fn NaN bytes contribute 0 (the reference kernels' rule); e5m2
  * operands follow IEEE arithmetic (inf and NaN propagate into the fp32 sum).  M <= 16 runs the warp-MMA GEMV
  * (all four type pairs), larger M the tcgen05 GEMM (formats are two bits of the instruction descriptor).

@@ -56,6 +56,9 @@ def capi():
     L.fp8b_scaled_mm_workspace_bytes.argtypes = [i32, i32, i32]
     L.fp8b_scaled_mm_select.restype = i32
     L.fp8b_scaled_mm_select.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64]
+    if hasattr(L, "fp8b_gemv_batch") or not os.environ.get("FP8B_LIB"):
+        L.fp8b_gemv_batch.restype = i32
+        L.fp8b_gemv_batch.argtypes = [vp, i32, i32, i32, i32, vp]
     if hasattr(L, "fp8b_scaled_mm_fmt") or not os.environ.get("FP8B_LIB"):
         L.fp8b_scaled_mm_fmt.restype = i32
         L.fp8b_scaled_mm_fmt.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp, i32, vp]
@@ -78,6 +81,13 @@ def capi():
 class Span(ctypes.Structure):
     """fp8b_span (include/fp8_b200.h)"""
     _fields_ = [("inp", ctypes.c_void_p), ("out", ctypes.c_void_p), ("n", ctypes.c_size_t)]
+
+
+class GemvItem(ctypes.Structure):
+    """fp8b_gemv_item (include/fp8_b200.h)"""
+    _fields_ = [("x", ctypes.c_void_p), ("W", ctypes.c_void_p), ("y", ctypes.c_void_p), ("N", ctypes.c_int),
+                ("scale_x", ctypes.c_void_p), ("scale_w", ctypes.c_void_p), ("scale_w_len", ctypes.c_int),
+                ("bias", ctypes.c_void_p)]
 
 
 def make_spans(triples):

@@ -543,3 +543,64 @@ def test_e5m2_through_patched_scaled_mm():
         fp8_mps_patch.uninstall()
     ref = o.scaled_mm(A, W, np.array([0.25], np.float32), np.array([0.5], np.float32), None, None, "f32", a_format="e5m2")
     _check(y, ref, None, what="patched e5m2")
+
+
+# ------------------------------------------------------------------ several GEMVs in one launch
+
+@pytest.mark.parametrize("K,Ns,odt,shared_x", [(4096, [4096, 1024, 1024], torch.bfloat16, True),
+                                               (14336, [4096, 300], None, False),
+                                               (1024, [8, 1, 77, 2048] * 5, torch.float16, False),   # 20 items: two launches
+                                               (16, [5], None, True)])
+def test_gemv_batch_matches_single_calls_and_oracle(K, Ns, odt, shared_x):
+    """fp8_scaled_mm_many == the M = 1 kernel called once per problem (same per-lane accumulation order, so
+    bit-identical whenever that call does not split K) and within tolerance of the oracle, incl. a NaN weight byte,
+    per-row weight scales and biases."""
+    import fp8_mps_native
+    g = torch.Generator().manual_seed(K + len(Ns))
+    xs, Ws, sxs, sws, bs = [], [], [], [], []
+    x0 = _rand_fp8((1, K), 11)
+    for i, N in enumerate(Ns):
+        x = x0 if shared_x else _rand_fp8((1, K), 20 + i)
+        W = _rand_fp8((N, K), 40 + i)
+        if i == 1:
+            W[0, min(5, K - 1)] = 0x7F                        # NaN byte: contributes 0 (metal:21)
+        xs.append(x); Ws.append(W)
+        sxs.append(np.array([0.02 + 0.01 * i], dtype=np.float32))
+        sws.append(((np.random.default_rng(i).random(N) + 0.5) * 0.01).astype(np.float32) if i % 2 else np.array([0.015], np.float32))
+        bs.append(torch.randn(N, generator=g).to(odt or torch.float32) if i % 3 == 0 else None)
+    to_dev = lambda a: torch.from_numpy(a).to(DEV)
+    ys = fp8_mps_native.fp8_scaled_mm_many([to_dev(x) for x in xs], [to_dev(W) for W in Ws], [to_dev(s) for s in sxs],
+                                           [to_dev(s) for s in sws], [None if b is None else b.to(DEV) for b in bs], odt)
+    assert len(ys) == len(Ns)
+    for i, N in enumerate(Ns):
+        assert ys[i].shape == (1, N) and ys[i].dtype == (odt or torch.float32)
+        ref = o.scaled_mm(xs[i], Ws[i], sxs[i], sws[i], None if bs[i] is None else to_np(bs[i]), None, dt_name(odt))
+        _check(ys[i], ref, odt, what=f"gemv batch item {i} N{N} K{K}")
+        single = fp8_mps_native.fp8_scaled_mm_fused(to_dev(xs[i]), to_dev(Ws[i]), to_dev(sxs[i]), to_dev(sws[i]),
+                                                    None if bs[i] is None else bs[i].to(DEV), None, odt, algo=1)
+        if N >= 2 * 148 * 8 or K < 4096:                      # the single call does not split K here: same summation order
+            assert torch.equal(ys[i], single), f"item {i}"
+    assert fp8_mps_native.fp8_scaled_mm_many([], [], [], []) == []
+
+
+def test_gemv_batch_validation():
+    from _util import GemvItem, capi, stream_ptr
+    L = capi()
+    x = torch.zeros(64, dtype=torch.uint8, device=DEV); W = torch.zeros(4, 64, dtype=torch.uint8, device=DEV)
+    y = torch.zeros(4, device=DEV); s = torch.ones(1, device=DEV)
+    def item(**kw):
+        it = (GemvItem * 1)()
+        d = dict(x=x.data_ptr(), W=W.data_ptr(), y=y.data_ptr(), N=4, scale_x=s.data_ptr(), scale_w=s.data_ptr(), scale_w_len=1, bias=None)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(it[0], k, v)
+        return it
+    assert L.fp8b_gemv_batch(item(), 1, 64, 0, 0, stream_ptr()) == 0
+    assert L.fp8b_gemv_batch(None, 0, 64, 0, 0, stream_ptr()) == 0
+    assert L.fp8b_gemv_batch(None, 1, 64, 0, 0, stream_ptr()) == -1
+    assert L.fp8b_gemv_batch(item(scale_w_len=3), 1, 64, 0, 0, stream_ptr()) == -1
+    assert L.fp8b_gemv_batch(item(W=None), 1, 64, 0, 0, stream_ptr()) == -1
+    assert L.fp8b_gemv_batch(item(), 1, 64, 7, 0, stream_ptr()) == -1
+    assert L.fp8b_gemv_batch(item(), 1, 24, 0, 0, stream_ptr()) == -2          # K % 16 != 0
+    assert L.fp8b_gemv_batch(item(x=x.data_ptr() + 1), 1, 48, 0, 0, stream_ptr()) == -2   # unaligned x
+    assert L.fp8b_gemv_batch(item(N=0), 1, 64, 0, 0, stream_ptr()) == 0
