@@ -447,6 +447,44 @@ void fp8_scaled_mm_peers(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a
     check_status(rc, "fp8b_scaled_mm_peers");
 }
 
+// N-sharded linear, fused compute + exchange with TMA stores (fp8b_scaled_mm_push).  `out` is this rank's (M, full_N)
+// buffer; `dst_ptrs` are the base addresses of the 1..8 destination buffers of that same geometry as mapped into this
+// process (torch symmetric memory `buffer_ptrs`; this rank's own buffer among them), in the order they should be
+// written.  The column block [n0, n0 + N) of every destination is written.
+void fp8_scaled_mm_push(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
+                        c10::optional<torch::Tensor> bias, torch::Tensor out, std::vector<int64_t> dst_ptrs, int64_t n0)
+{
+    TORCH_CHECK(A.dtype() == torch::kUInt8 && B.dtype() == torch::kUInt8, "A and B must be uint8 (FP8 encoded)");
+    TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous CUDA tensors");
+    TORCH_CHECK(A.dim() == 2 && B.dim() == 2 && A.size(1) == B.size(1), "K dimension mismatch between A and B");
+    TORCH_CHECK(out.is_cuda() && out.dim() == 2 && out.is_contiguous() && out.size(0) == A.size(0), "out must be (M, full_N) contiguous");
+    TORCH_CHECK(!dst_ptrs.empty() && dst_ptrs.size() <= 8, "need 1..8 destination buffers");
+    const int64_t M = A.size(0), K = A.size(1), N = B.size(0), full_N = out.size(1);
+    TORCH_CHECK(n0 >= 0 && n0 + N <= full_N, "column block outside the full matrix");
+    c10::cuda::CUDAGuard guard(A.device());
+    torch::Tensor sa_t, sb_t, bias_t;
+    int64_t sa_len = 0, sb_len = 0;
+    const float* sa = scale_ptr(scale_a, A.device(), sa_t, sa_len);
+    const float* sb = scale_ptr(scale_b, A.device(), sb_t, sb_len);
+    const void* bias_ptr = nullptr;
+    int bias_dt = FP8B_F32;
+    if (bias.has_value() && bias->defined()) {
+        bias_t = bias->to(A.device()).contiguous().reshape({-1});
+        if (bias_t.scalar_type() != at::kFloat && bias_t.scalar_type() != at::kHalf && bias_t.scalar_type() != at::kBFloat16)
+            bias_t = bias_t.to(torch::kFloat32);
+        TORCH_CHECK(bias_t.numel() == N, "bias must have N elements");
+        bias_ptr = bias_t.data_ptr();
+        bias_dt = to_fp8b_dtype(bias_t.scalar_type());
+    }
+    void* dsts[8];
+    for (size_t d = 0; d < dst_ptrs.size(); ++d)
+        dsts[d] = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(dst_ptrs[d])) + n0 * out.element_size();
+    int rc = fp8b_scaled_mm_push(u8_ptr(A), u8_ptr(B), dsts, (int)dst_ptrs.size(), to_fp8b_dtype(out.scalar_type()),
+                                 (int)M, (int)N, (int)K, full_N, sa, (int)sa_len, sb, (int)sb_len, bias_ptr, bias_dt, nullptr,
+                                 current_stream());
+    check_status(rc, "fp8b_scaled_mm_push");
+}
+
 // per-row fp8_quantize of a 2-D tensor: returns (uint8 (rows, cols), inv_scale float32 [rows])
 std::tuple<torch::Tensor, torch::Tensor> fp8_quantize_rowwise(torch::Tensor input)
 {
@@ -556,6 +594,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
           "FP8 scaled matmul storing its tiles into every rank's symmetric buffer with peer stores (N-sharded linear)",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out"),
           py::arg("peer_deltas"), py::arg("n0"));
+    m.def("fp8_scaled_mm_push", &fp8_scaled_mm_push,
+          "N-sharded linear: tcgen05 GEMM whose TMA-store epilogue pushes each tile into every destination buffer",
+          py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out"),
+          py::arg("dst_ptrs"), py::arg("n0"));
+    m.def("push_supported", [](int64_t M, int64_t N, int64_t K, int64_t ldc, at::ScalarType dt) {
+        // alignment of torch allocations (>= 256 B) is assumed; this answers the shape part
+        return fp8b_scaled_mm_push_supported(to_fp8b_dtype(dt), (int)M, (int)N, (int)K, ldc, nullptr, nullptr, nullptr) != 0;
+    });
     m.def("select_algo", &select_algo, py::arg("A"), py::arg("B"), py::arg("out_dtype"));
     m.def("launch_count", []() { return (uint64_t)fp8b_launch_count(); });
     m.def("set_option", [](int option, int value) { check_status(fp8b_set_option(option, value), "fp8b_set_option"); });

@@ -34,11 +34,23 @@ const DeviceInfo& device_info()
     return info[dev];
 }
 
-int tune_int(const char* name, int dflt)
+static int env_int(const char* name, int dflt)
 {
     const char* v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
+#ifdef FP8B_PROFILE
+int tune_int(const char* name, int dflt) { return env_int(name, dflt); }
+#endif
+
+std::atomic<int> g_tune[kTuneCount];
+namespace {
+const char* const kTuneEnv[kTuneCount] = {"FP8B_GEMM_CFG", "FP8B_GEMV_IMPL", "FP8B_DYNAMIC_PLAN", "FP8B_CAST_SHAPE",
+                                          "FP8B_GEMM_STORE", "FP8B_GEMV_UNROLL", "FP8B_GEMV_BATCH", "FP8B_AMAX_CAP"};
+struct TuneInit {
+    TuneInit() { for (int k = 0; k < kTuneCount; ++k) g_tune[k].store(env_int(kTuneEnv[k], -1)); }
+} g_tune_init;
+}  // namespace
 
 static int validate(const MMArgs& a)
 {
@@ -84,7 +96,12 @@ extern "C" int fp8b_set_option(int option, int value)
     switch (option) {
         case FP8B_OPT_PDL: g_opt_pdl.store(value ? 1 : 0); return FP8B_OK;
         case FP8B_OPT_STATIC_WEIGHTS: g_opt_static_weights.store(value ? 1 : 0); return FP8B_OK;
-        default: return FP8B_ERR_INVALID;
+        default:
+            if (option >= FP8B_OPT_TUNE_GEMM_CFG && option < FP8B_OPT_TUNE_GEMM_CFG + kTuneCount) {
+                g_tune[option - FP8B_OPT_TUNE_GEMM_CFG].store(value < 0 ? -1 : value);
+                return FP8B_OK;
+            }
+            return FP8B_ERR_INVALID;
     }
 }
 
@@ -93,7 +110,10 @@ extern "C" int fp8b_get_option(int option)
     switch (option) {
         case FP8B_OPT_PDL: return g_opt_pdl.load();
         case FP8B_OPT_STATIC_WEIGHTS: return g_opt_static_weights.load();
-        default: return FP8B_ERR_INVALID;
+        default:
+            if (option >= FP8B_OPT_TUNE_GEMM_CFG && option < FP8B_OPT_TUNE_GEMM_CFG + kTuneCount)
+                return g_tune[option - FP8B_OPT_TUNE_GEMM_CFG].load();
+            return FP8B_ERR_INVALID;
     }
 }
 
@@ -221,7 +241,7 @@ extern "C" int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B,
     // M > 16: the same quantise kernel, then the shape-selected GEMM (tcgen05 when TMA-able) with per-row
     // scale_a.  Converting inside the GEMM's producer stage instead would redo the encode once per N-tile
     // column (48x for C4) on data that is read from L2 anyway; one 6 us pass over A is cheaper.
-    const int plan = tune_int("FP8B_DYNAMIC_PLAN", 0);         // 1 = force single kernel, 2 = force chain
+    const int plan = tune(kTuneDynamicPlan, 0);         // 1 = force single kernel, 2 = force chain
     if (have_ws && (plan != 1 || M > 16)) {
         uint8_t* q = static_cast<uint8_t*>(workspace);
         float* inv = inv_scale_a_out ? inv_scale_a_out
@@ -260,4 +280,37 @@ extern "C" int fp8b_scaled_mm_peers(const uint8_t* A, const uint8_t* B, void* C_
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
     if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
     return launch_gemm_tcgen05(a);
+}
+
+// N-sharded linear, fused compute + exchange with TMA stores: see include/fp8_b200.h.
+extern "C" int fp8b_scaled_mm_push(const uint8_t* A, const uint8_t* B, void* const* C_dsts, int n_dst,
+                                   int out_dtype, int M, int N, int K, int64_t ldc,
+                                   const float* scale_a, int scale_a_len,
+                                   const float* scale_b, int scale_b_len,
+                                   const void* bias, int bias_dtype,
+                                   const float* scale_result, void* stream)
+{
+    if (n_dst < 1 || n_dst > 8 || !C_dsts) return FP8B_ERR_INVALID;
+    for (int d = 0; d < n_dst; ++d)
+        if (!C_dsts[d]) return FP8B_ERR_INVALID;
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C_dsts[0]; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = const_cast<void**>(C_dsts); a.ws_bytes = (size_t)n_dst * sizeof(void*); a.st = (cudaStream_t)stream;
+    a.store_mc = 3 | (n_dst << 8);
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (M == 0 || N == 0) return FP8B_OK;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    return launch_gemm_tcgen05(a);
+}
+
+extern "C" int fp8b_scaled_mm_push_supported(int out_dtype, int M, int N, int K, int64_t ldc, const void* A, const void* B,
+                                             const void* C)
+{
+    if (M < 1 || N < 1 || K < 16 || (K % 16) != 0 || !valid_dtype(out_dtype) || ldc < N) return 0;
+    if (!aligned(A, 16) || !aligned(B, 16) || !aligned(C, 16)) return 0;
+    return ((size_t)ldc * dtype_size(out_dtype)) % 16 == 0 ? 1 : 0;
 }

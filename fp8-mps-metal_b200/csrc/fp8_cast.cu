@@ -594,7 +594,7 @@ struct CastShape { int big; int grid; };
 static CastShape cast_shape(size_t nvec) {
     const DeviceInfo& di = device_info();
     CastShape c;
-    const int mode = tune_int("FP8B_CAST_SHAPE", 0);          // profiling knob: 1 = always small tiles, 2 = always big
+    const int mode = tune(kTuneCastShape, 0);          // profiling knob: 1 = always small tiles, 2 = always big
     c.big = mode == 2 || (mode == 0 && nvec >= (size_t)di.sm_count * 4096);
     const size_t tile = c.big ? 4096 : 1024;
     size_t tiles = (nvec + tile - 1) / tile;
@@ -733,7 +733,7 @@ static int launch_amax(const void* in, size_t n, uint32_t* scratch, cudaStream_t
 {
     constexpr int EPV = (IN == FP8B_F32) ? 4 : 8;
     if (aligned(in, 16)) {
-        const size_t cap = (size_t)device_info().sm_count * tune_int("FP8B_AMAX_CAP", 8);
+        const size_t cap = (size_t)device_info().sm_count * tune(kTuneAmaxCap, 8);
         const size_t want = (n / EPV + kCastThreads * 4 - 1) / (kCastThreads * 4) + 1;
         amax_kernel<IN><<<(int)(want < cap ? want : cap), kCastThreads, 0, st>>>(in, n, scratch);
     }

@@ -25,9 +25,17 @@ inline int after_launch() {
 struct DeviceInfo { int sm_count; int cc_major; int cc_minor; int ok; };
 const DeviceInfo& device_info();
 
-// Developer tuning knob: integer from the environment (read on every call; used by the
-// profiling scripts to A/B kernel variants without rebuilding).  Never changes results.
-int tune_int(const char* name, int dflt);
+// Developer tuning knobs (fp8b_set_option, option ids FP8B_OPT_TUNE_*): choose between result-identical kernel
+// variants so that tests and profiling scripts can A/B them without rebuilding.  Each starts from the environment
+// variable of the same name (FP8B_GEMM_CFG, ...) read ONCE when the library is loaded -- never per call -- and none
+// of them can change a result.  -1 = unset (use the built-in rule).
+enum TuneKnob { kTuneGemmCfg = 0, kTuneGemvImpl, kTuneDynamicPlan, kTuneCastShape, kTuneGemmStore, kTuneGemvUnroll,
+                kTuneGemvBatch, kTuneAmaxCap, kTuneCount };
+extern std::atomic<int> g_tune[kTuneCount];
+inline int tune(TuneKnob k, int dflt) { const int v = g_tune[k].load(std::memory_order_relaxed); return v < 0 ? dflt : v; }
+#ifdef FP8B_PROFILE
+int tune_int(const char* name, int dflt);      // profiling builds only: environment, read per call
+#endif
 
 // Library options (fp8b_set_option)
 extern std::atomic<int> g_opt_pdl;

@@ -39,29 +39,61 @@ constexpr int kUmmaK = 32;        // bytes of K per tcgen05.mma (kind::f8f6f4)
 #endif
 constexpr int kNumEpiWarps = FP8B_EPI_WARPS;
 constexpr int kEpiColSplits = kNumEpiWarps / 4;
-constexpr int kGemmThreads = 64 + 32 * kNumEpiWarps;
+// How the epilogue gets the tile to memory (template parameter MODE):
+//   kStDirect  epilogue warps store with st.global (or multimem.st when C is a multicast address)
+//   kStPeers   epilogue warps store every piece locally and into each peer's buffer with st.global (round-1 plan)
+//   kStTma     epilogue warps only fill a swizzled shared-memory ring; a dedicated STORE warp pushes each
+//              128-row x 128-byte box with cp.async.bulk.tensor (TMA store) to 1..8 destinations -- this rank's
+//              buffer and, over NVLink, the same place in every peer's buffer.  The epilogue warps never wait on
+//              the memory system, so the accumulator goes back to the MMA warp as soon as TMEM is drained.
+enum { kStDirect = 0, kStPeers = 1, kStTma = 2 };
+constexpr int kMaxDst = 8;
+template <int MODE> constexpr int gemm_threads() { return 64 + 32 * kNumEpiWarps + (MODE == kStTma ? 32 : 0); }
+constexpr int kStoreBoxBytes = 128 * 128;       // one TMA-store box: 128 rows x 128 bytes, 128B-swizzled
+constexpr int kStoreInflight = 2;               // TMA-store groups that may still be reading shared memory
 // Warp roles.  The epilogue takes the LOW warp ids and the two single-thread roles the HIGH ones: the warp
 // scheduler favours higher warp ids among eligible warps, and the MMA issuer / TMA producer are latency-critical
 // (with the roles the other way round the epilogue's ALU stream delayed MMA issue: 14.2K vs 12.4K cycles per tile).
 constexpr int kWarpEpi0 = 0;                    // warps 0..kNumEpiWarps-1: epilogue (TMEM lane quarter = warp % 4)
 constexpr int kWarpTma = kNumEpiWarps;          // TMA producer
 constexpr int kWarpMma = kNumEpiWarps + 1;      // MMA issuer
+constexpr int kWarpStore = kNumEpiWarps + 2;    // kStTma only: TMA-store issuer
+
+// Profiling knobs (FP8B_GEMM_DEBUG bits, per-tile clock stamps) exist only in -DFP8B_PROFILE builds: the shipped
+// library has no run-time switch that can change a result.
+#ifdef FP8B_PROFILE
+#define FP8B_DBG(p, bits) ((p).debug & (bits))
+#else
+#define FP8B_DBG(p, bits) 0
+#endif
 
 // CG = CTA-group size.  CG == 2: two CTAs of a cluster (an SM pair) compute one 256 x BN tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, so the
 // shared-memory traffic per MMA (operand reads + TMA writes) drops from 24 KB to 16 KB per 128 cycles.
-template <int BN, int CG> struct GemmCfg {
+template <int BN, int CG, int MODE = kStDirect> struct GemmCfg {
     static constexpr int kABytes = kBM * kBK;
     static constexpr int kBRows = BN / CG;                         // B rows staged by one CTA
     static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kEpiStageBytes = kNumEpiWarps * 8192;    // per epilogue warp: 32 rows x 256 B, XOR-swizzled
+    static constexpr int kStoreSlots = 4;                          // kStTma: ring of TMA-store boxes
+    // epilogue staging: per epilogue warp 32 rows x 256 B, XOR-swizzled -- or the TMA-store ring
+    static constexpr int kEpiStageBytes = MODE == kStTma ? kStoreSlots * kStoreBoxBytes : kNumEpiWarps * 8192;
     static constexpr int kStagesFit = (232448 - 1024 - 256 - kEpiStageBytes) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;   // two accumulators; a power of two >= 32
     static constexpr int kBarBytes = 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiStageBytes + 1024;   // +1024: manual alignment
+    // layout: [operand ring | epilogue staging (1024-byte aligned) | barriers]
+    static constexpr int kOffStaging = kStages * kStageBytes;
+    static constexpr int kOffBar = kOffStaging + kEpiStageBytes;
+    static constexpr int kSmemBytes = kOffBar + kBarBytes + 1024;   // +1024: manual alignment
+    static_assert(kStageBytes % 1024 == 0, "operand stages must keep the 1024-byte swizzle alignment");
+    static_assert((2 * kStages + 4 + 2 * kStoreSlots) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
+
+struct StoreMaps { CUtensorMap m[kMaxDst]; };    // kStTma: one byte-typed map per destination buffer
+struct NoStoreMaps { int unused; };
+template <int MODE> struct StoreMapsOf { using type = NoStoreMaps; };
+template <> struct StoreMapsOf<kStTma> { using type = StoreMaps; };
 
 struct GemmParams {
     const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
@@ -72,11 +104,12 @@ struct GemmParams {
     Epi epi;
     int vec_store_ok;                        // C base and ldc allow 16-byte row-chunk stores
     int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
-    int store_mc;                            // C is an NVSwitch multicast address: store with multimem.st
-    long long* dbg;                          // FP8B_GEMM_DEBUG & 16: per-tile clock64 stamps of CTA 0 (profiling only)
-    int debug;                               // bits 0-7: FP8B_GEMM_DEBUG profiling knob (1 = no stores, 2 = drain TMEM only);
-                                             // bit 8 / bit 9: A / B operand is e5m2 (kept in this word so that the
-                                             // parameter block -- and with it the tuned schedule -- does not change)
+    int store_mc;                            // bits 0-7: 1 = C is an NVSwitch multicast address (multimem.st);
+                                             // bits 8+: number of destinations (kStPeers / kStTma)
+    long long* aux;                          // kStPeers: device table of per-rank byte deltas.  FP8B_PROFILE builds,
+                                             // FP8B_GEMM_DEBUG & 16: per-tile clock64 stamps of CTA 0
+    int debug;                               // bits 0-7: FP8B_GEMM_DEBUG profiling knob (FP8B_PROFILE builds only);
+                                             // bit 8 / bit 9: A / B operand is e5m2
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -128,6 +161,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+
+// TMA store of one box from shared memory (bulk async-group completion).  The tensor map may describe local HBM or
+// a peer GPU's buffer mapped into this process: the copy engine of the SM does the NVLink writes.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
@@ -275,18 +320,70 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
 
 // ------------------------------------------------------------------------------ kernel
 
-// PEERS: the epilogue stores every 16-byte piece once per GPU of an N-sharded linear -- into this rank's buffer and,
-// as plain st.global over NVLink, into the peers' symmetric buffers (byte deltas from the local address in a small
-// device table, GemmParams::dbg).  Unlike the multicast mode, a rank's own shard does not travel through the
-// switch and back.  A separate instantiation, so the single-GPU and multicast kernels are untouched.
-template <int BN, int CG, bool PEERS = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// Per-column epilogue parameters of one 32-column chunk, loaded while the TMEM load is in flight: one broadcast
+// 16-byte load per 4 columns when the chunk is full and the arrays are aligned, guarded scalar loads at the N edge.
+__device__ __forceinline__ void load_col_params(const Epi& e, int n0, int N, bool vec, float (&sbv)[32], float (&bv)[32]) {
+    if (vec) {
+        if (e.sb_stride) {
+            const float4* s4 = reinterpret_cast<const float4*>(e.sb + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = s4[j];
+                sbv[4 * j] = t.x; sbv[4 * j + 1] = t.y; sbv[4 * j + 2] = t.z; sbv[4 * j + 3] = t.w;
+            }
+        }
+        if (e.bias) {
+            if (e.bias_dtype == FP8B_F32) {
+                const float4* b4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.bias) + n0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = b4[j];
+                    bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
+                }
+            } else {
+                const uint4* b4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.bias) + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 t = b4[j];
+                    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (e.bias_dtype == FP8B_BF16) {
+                            bv[8 * j + 2 * i] = __uint_as_float(w[i] << 16);
+                            bv[8 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+                        } else {
+                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                            bv[8 * j + 2 * i] = f.x; bv[8 * j + 2 * i + 1] = f.y;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            const bool ok = n < N;
+            sbv[j] = (e.sb_stride && ok) ? e.sb[n] : 0.0f;
+            bv[j] = (e.bias && ok) ? epi_bias(e, n) : 0.0f;
+        }
+    }
+}
+
+// MODE (see the enum above) selects how tiles leave the SM.  kStPeers / kStTma are separate instantiations, so the
+// single-GPU and multicast kernels are untouched by the multi-destination code.
+template <int BN, int CG, int MODE = kStDirect>
+__global__ void __launch_bounds__(gemm_threads<MODE>(), 1)
 fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ typename StoreMapsOf<MODE>::type smaps,
                         const GemmParams p)
 {
-    using Cfg = GemmCfg<BN, CG>;
-    long long* const dbg = PEERS ? nullptr : p.dbg;  // (PEERS: the field carries the peer delta table instead)
+    using Cfg = GemmCfg<BN, CG, MODE>;
+    constexpr bool PEERS = MODE == kStPeers;
+#ifdef FP8B_PROFILE
+    long long* const dbg = PEERS ? nullptr : p.aux;  // (PEERS: the field carries the peer delta table instead)
+#endif
     constexpr int kTileM = kBM * CG;                 // rows of C per tile (per CTA pair when CG == 2)
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool is_leader = cta_rank == 0;
@@ -294,16 +391,19 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int num_workers = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* bar_mem = smem + Cfg::kStages * Cfg::kStageBytes;
+    uint8_t* bar_mem = smem + Cfg::kOffBar;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bar_mem);
-    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    // barrier slots (8 bytes each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], sfull[slots], sfree[slots]
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * Cfg::kStages + 2 + a); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(bar_mem + 8 * (2 * Cfg::kStages + 4));
-    const uint32_t stage_base = bar_base + Cfg::kBarBytes;         // epilogue staging tiles (16-byte aligned)
+    auto sfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 4 + s); };
+    auto sfree_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + 4 + Cfg::kStoreSlots + s); };
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(bar_mem + 8 * (2 * Cfg::kStages + 4 + 2 * Cfg::kStoreSlots));
+    const uint32_t stage_base = smem_base + Cfg::kOffStaging;      // epilogue staging (1024-byte aligned)
 
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -315,6 +415,8 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps * CG); }
+        if (MODE == kStTma)
+            for (int s = 0; s < Cfg::kStoreSlots; ++s) { mbar_init(sfull_bar(s), kNumEpiWarps); mbar_init(sfree_bar(s), 1); }
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -336,7 +438,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         {
             const bool elected = elect_one();
             int stage = 0; uint32_t phase = 0;
+#ifdef FP8B_PROFILE
             int issued = 0;
+#endif
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const TileCoord tc = decode_tile(p, tile, BN);
                 const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
@@ -347,10 +451,13 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
                     if (elected) {
+#ifdef FP8B_PROFILE
                         if ((p.debug & 32) && issued >= Cfg::kStages) {
                             // profiling only: no TMA traffic after the ring is primed (results are garbage)
                             if (is_leader) mbar_arrive(full_bar(stage));
-                        } else if (CG == 2) {
+                        } else
+#endif
+                        if (CG == 2) {
                             // both CTAs load their halves; all bytes are accounted on the leader's barrier
                             if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
                             tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
@@ -362,7 +469,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         }
                     }
                     __syncwarp();
+#ifdef FP8B_PROFILE
                     ++issued;
+#endif
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -382,10 +491,14 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
+#ifdef FP8B_PROFILE
                 const long long t_m0 = (dbg && blockIdx.x == 0) ? clock64() : 0;
+#endif
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);           // epilogue has drained this accumulator
                 tc_fence_after();
+#ifdef FP8B_PROFILE
                 const long long t_m1 = (dbg && blockIdx.x == 0) ? clock64() : 0;
+#endif
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 const uint32_t idesc_t = ((tile < p.full_tiles) ? idesc : make_idesc(kTileM, BN / 2)) | idesc_fmt;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -407,12 +520,156 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 if (elected) {
                     if (CG == 2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));   // accumulator complete
+#ifdef FP8B_PROFILE
                     if (dbg && blockIdx.x == 0) {
                         const int ti = (tile - worker) / num_workers;
                         if (ti < 64) { dbg[ti * 8 + 0] = t_m0; dbg[ti * 8 + 1] = t_m1; dbg[ti * 8 + 2] = clock64(); dbg[ti * 8 + 3] = 0; }
                     }
+#endif
                 }
                 __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (MODE == kStTma && warp == kWarpStore) {
+        // ===================== TMA-store issuer (kStTma) =====================
+        // Walks the same (tile, box) sequence as the epilogue warps.  Per box: wait until the four epilogue warps
+        // have filled the slot, issue one TMA store per destination, commit; then recycle the slot whose stores have
+        // finished READING shared memory (the writes themselves stay in flight).
+        if constexpr (MODE == kStTma) {
+            const bool elected = elect_one();
+            const int n_dst = p.store_mc >> 8;
+            const int esz = p.epi.out_dtype == FP8B_F32 ? 4 : 2;
+            const int cols_per_box = 128 / esz;
+            uint32_t seq = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+                for (int c = 0; c < tc.width; c += cols_per_box) {
+                    const int n_box = tc.n0 + c;
+                    if (n_box >= p.N) break;                      // warp-uniform; the epilogue skips the same boxes
+                    const uint32_t slot = seq % Cfg::kStoreSlots;
+                    mbar_wait(sfull_bar(slot), (seq / Cfg::kStoreSlots) & 1);
+                    if (elected) {
+                        if (m_idx < p.M) {
+                            const uint32_t src = stage_base + slot * kStoreBoxBytes;
+                            for (int d = 0; d < n_dst; ++d) tma_store_2d(&smaps.m[d], src, n_box * esz, m_idx);
+                        }
+                        bulk_commit_group();
+                        bulk_wait_group_read<kStoreInflight>();
+                        if (seq >= (uint32_t)kStoreInflight) mbar_arrive(sfree_bar((seq - kStoreInflight) % Cfg::kStoreSlots));
+                    }
+                    __syncwarp();
+                    ++seq;
+                }
+            }
+            if (elected) bulk_wait_group_all();                   // all writes performed before the CTA retires
+            __syncwarp();
+        }
+    } else if (MODE == kStTma) {
+        // ===================== epilogue, TMA-store flavour (warps 0..3) =====================
+        // tcgen05.ld -> scale/bias -> out dtype -> 128B-swizzled box in shared memory.  Lane = row; a 16-byte piece
+        // j of row r lives at r*128 + ((j ^ (r & 7)) * 16): conflict-free st.shared.v4 and exactly the layout the
+        // SWIZZLE_128B tensor map of the store expects.  Column/row edges need no code: TMA clips the box.
+        if constexpr (MODE == kStTma) {
+            const int q = warp & 3;
+            const int row_in_tile = q * 32 + lane;
+            const Epi& e = p.epi;
+            const float sr = e.sr ? *e.sr : 1.0f;
+            const float sb0 = e.sb[0];
+            const bool is_f32 = e.out_dtype == FP8B_F32;
+            const int cols_per_box = is_f32 ? 32 : 64;
+            const uint32_t row_off = (uint32_t)row_in_tile * 128u;
+            uint32_t seq = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+                const int n_idx = tc.n0;
+                const int m = m_idx + row_in_tile;
+                const bool m_ok = m < p.M;
+                const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < tc.width; c0 += 32) {
+                    uint32_t r[32];
+                    __syncwarp();
+                    tmem_ld_x32(t_row + c0, r);
+                    const int n0 = n_idx + c0;
+                    const int n_box = n_idx + (c0 & ~(cols_per_box - 1));
+                    const bool box_first = (c0 & (cols_per_box - 1)) == 0;
+                    const bool box_last = ((c0 + 32) & (cols_per_box - 1)) == 0;
+                    const bool box_ok = n_box < p.N;                                   // warp-uniform
+                    const bool chunk_ok = n0 < p.N;
+                    float sbv[32];
+                    float bv[32];
+                    if (chunk_ok) load_col_params(e, n0, p.N, (n0 + 32 <= p.N) && p.col_vec_ok, sbv, bv);
+                    const uint32_t slot = seq % Cfg::kStoreSlots;
+                    if (box_ok && box_first) mbar_wait(sfree_bar(slot), ((seq / Cfg::kStoreSlots) & 1) ^ 1);
+                    tmem_ld_wait();
+                    if (c0 + 32 == tc.width) {              // last read of this accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+                    }
+                    if (!box_ok) continue;
+                    if (chunk_ok) {
+                        // NaN-byte fix-up (cold): a NaN accumulator can only come from a 0x7F/0xFF operand byte
+                        float nan_probe = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) nan_probe += __uint_as_float(r[j]);
+                        if (__any_sync(0xFFFFFFFFu, nan_probe != nan_probe)) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float a = __uint_as_float(r[j]);
+                                if (a != a && m_ok && n0 + j < p.N)
+                                    r[j] = __float_as_uint(slow_dot_fmt(p.A + (size_t)m * p.K, p.B + (size_t)(n0 + j) * p.K, p.K,
+                                                                        (p.debug >> 8) & 1, (p.debug >> 9) & 1));
+                            }
+                        }
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __fmul_rn(__uint_as_float(r[j]), sa);
+                            x = __fmul_rn(x, e.sb_stride ? sbv[j] : sb0);
+                            if (e.bias) x = __fadd_rn(x, bv[j]);
+                            if (e.sr) x = __fmul_rn(x, sr);
+                            v[j] = x;
+                        }
+                        const uint32_t dst = stage_base + slot * kStoreBoxBytes + row_off;
+                        const uint32_t sw = (uint32_t)(lane & 7);
+                        if (is_f32) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                sts_v4(dst + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                        } else {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                if (e.out_dtype == FP8B_BF16) {
+                                    __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                    pk[j] = *reinterpret_cast<uint32_t*>(&b);
+                                } else {
+                                    __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                                    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                                }
+                            }
+                            const uint32_t piece0 = (uint32_t)((c0 & 32) >> 3);        // 0 or 4: which half of the 128-byte row
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                sts_v4(dst + (((piece0 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        }
+                    }
+                    if (box_last || c0 + 32 == tc.width) {
+                        fence_proxy_async_smem();           // generic-proxy writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(sfull_bar(slot));
+                        ++seq;
+                    }
+                }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -420,7 +677,6 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         // ===================== epilogue (warps 0..3) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may read (warp id % 4)
         const int col_part = (warp - kWarpEpi0) >> 2;         // which slice of the tile's columns this warp drains
-        constexpr int kColsPerWarp = BN / kEpiColSplits;
         const int row_in_tile = q * 32 + lane;
         const Epi& e = p.epi;
         const float sr = e.sr ? *e.sr : 1.0f;
@@ -429,7 +685,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int peer_world = PEERS ? (p.store_mc >> 8) : 0;
         if (PEERS) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) peer_delta[r] = r < peer_world ? p.dbg[r] : 0;
+            for (int r = 0; r < 8; ++r) peer_delta[r] = r < peer_world ? p.aux[r] : 0;
         }
         auto store16 = [&](void* ptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
             if (PEERS) {
@@ -437,7 +693,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 for (int r = 0; r < 8; ++r)
                     if (r < peer_world) stg_v4(reinterpret_cast<uint8_t*>(ptr) + peer_delta[r], a, b, c, d, 0);
             } else {
-                stg_v4(ptr, a, b, c, d, p.store_mc);
+                stg_v4(ptr, a, b, c, d, p.store_mc & 1);
             }
         };
         int acc = 0; uint32_t acc_phase = 0;
@@ -445,14 +701,18 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const TileCoord tc = decode_tile(p, tile, BN);
             const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
             const int n_idx = tc.n0;
-            const int cols_per_warp = tc.width / kEpiColSplits;      // kColsPerWarp, or half of it in the split last wave
+            const int cols_per_warp = tc.width / kEpiColSplits;      // BN / splits, or half of it in the split last wave
             const int m = m_idx + row_in_tile;
             const bool m_ok = m < p.M;
             const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
+#ifdef FP8B_PROFILE
             const long long t_e0 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+#endif
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+#ifdef FP8B_PROFILE
             const long long t_e1 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+#endif
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
             for (int c0 = col_part * cols_per_warp; c0 < (col_part + 1) * cols_per_warp; c0 += 32) {
@@ -461,47 +721,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 tmem_ld_x32(t_row + c0, r);
                 const int n0 = n_idx + c0;
                 const bool full_chunk = (n0 + 32 <= p.N) && p.col_vec_ok;      // warp-uniform
-                // per-column parameters of this chunk: one broadcast 16-byte load per 4 columns, issued
-                // while the TMEM load is in flight
                 float sbv[32];
                 float bv[32];
-                if (full_chunk) {
-                    if (e.sb_stride) {
-                        const float4* s4 = reinterpret_cast<const float4*>(e.sb + n0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 t = s4[j];
-                            sbv[4 * j] = t.x; sbv[4 * j + 1] = t.y; sbv[4 * j + 2] = t.z; sbv[4 * j + 3] = t.w;
-                        }
-                    }
-                    if (e.bias) {
-                        if (e.bias_dtype == FP8B_F32) {
-                            const float4* b4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.bias) + n0);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t = b4[j];
-                                bv[4 * j] = t.x; bv[4 * j + 1] = t.y; bv[4 * j + 2] = t.z; bv[4 * j + 3] = t.w;
-                            }
-                        } else {
-                            const uint4* b4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(e.bias) + n0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint4 t = b4[j];
-                                const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    if (e.bias_dtype == FP8B_BF16) {
-                                        bv[8 * j + 2 * i] = __uint_as_float(w[i] << 16);
-                                        bv[8 * j + 2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-                                    } else {
-                                        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-                                        bv[8 * j + 2 * i] = f.x; bv[8 * j + 2 * i + 1] = f.y;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
+                if (full_chunk) load_col_params(e, n0, p.N, true, sbv, bv);
                 tmem_ld_wait();
                 if (c0 + 32 == (col_part + 1) * cols_per_warp) {   // this warp's last read of the accumulator: hand it back early
                     tc_fence_before();
@@ -509,7 +731,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
                 }
                 if (n0 >= p.N) continue;              // warp-uniform
-                if (p.debug & 2) continue;
+                if (FP8B_DBG(p, 2)) continue;
 
                 // NaN-byte fix-up (cold): a NaN accumulator can only come from a 0x7F/0xFF operand byte
                 float nan_probe = 0.0f;
@@ -564,7 +786,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const int rel = (c0 - col_part * cols_per_warp) >> 5; // chunk index inside this warp's span
                     const int cg = rel & (cpg - 1);                      // chunk index inside its group
                     const int ng0 = n0 - cg * 32;                        // first column of the group
-                    const bool staged = !(p.debug & 1) && (ng0 + cpg * 32 <= p.N) && !(p.debug & 4) &&
+                    const bool staged = !FP8B_DBG(p, 1 | 4) && (ng0 + cpg * 32 <= p.N) &&
                                         ((rel - cg + cpg) * 32 <= cols_per_warp);   // warp-uniform; the whole group lies in this warp's span
                     if (staged) {
                         const uint32_t wbase = stage_base + (uint32_t)(warp - kWarpEpi0) * 8192u;
@@ -592,7 +814,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             }
                             __syncwarp();
                         }
-                    } else if (m_ok && !(p.debug & 1)) {
+                    } else if (m_ok && !FP8B_DBG(p, 1)) {
                         uint8_t* dst = reinterpret_cast<uint8_t*>(e.C) + ((size_t)m * e.ldc + n0) * (is_f32 ? 4 : 2);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -607,10 +829,12 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     }
                 }
             }
+#ifdef FP8B_PROFILE
             if (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) {
                 const int ti = (tile - worker) / num_workers;
                 if (ti < 64) { dbg[ti * 8 + 4] = t_e0; dbg[ti * 8 + 5] = t_e1; dbg[ti * 8 + 6] = clock64(); }
             }
+#endif
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -623,6 +847,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
+
 
 // ------------------------------------------------------------------------------ host side
 
@@ -644,19 +869,49 @@ static PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-// rows x K bytes, row-major; box = box_rows x 128 bytes, 128B swizzle.
-static bool encode_operand_map(CUtensorMap* map, const uint8_t* base, int rows, int K, int box_rows)
+// A tensor map is a pure function of (base, rows, row bytes, pitch, box): a serving loop calls the same few
+// weights and buffers over and over, so the encoded maps are kept in a small per-thread direct-mapped cache (the
+// analogue of the reference bridge's one-time pipeline cache, fp8_bridge.cpp:103-141).  A map holds only addresses
+// and extents, never data, so a stale entry for a freed-and-reallocated pointer with the same geometry is still right.
+struct MapKey {
+    const void* base; uint64_t rows, row_bytes, pitch; uint32_t box_rows, box_bytes;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && rows == o.rows && row_bytes == o.row_bytes && pitch == o.pitch &&
+               box_rows == o.box_rows && box_bytes == o.box_bytes;
+    }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
+constexpr int kMapCacheSlots = 64;
+
+// rows x row_bytes uint8 matrix with a row pitch, box = box_rows x box_bytes (<= 128), 128B swizzle.
+static bool get_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t pitch,
+                           uint32_t box_rows, uint32_t box_bytes)
 {
+    static thread_local MapSlot cache[kMapCacheSlots];
+    const MapKey key = {base, rows, row_bytes, pitch, box_rows, box_bytes};
+    uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
+    h ^= rows * 0x9E3779B97F4A7C15ull; h ^= row_bytes * 0xC2B2AE3D27D4EB4Full; h ^= pitch << 7; h ^= (uint64_t)box_rows << 40;
+    h ^= h >> 29;
+    MapSlot& s = cache[h % kMapCacheSlots];
+    if (s.valid && s.key == key) { *out = s.map; return true; }
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
+    if (r != CUDA_SUCCESS) return false;
+    s.key = key; s.map = *out; s.valid = true;
+    return true;
+}
+
+// operand: rows x K bytes, row-major; box = box_rows x 128 bytes
+static bool encode_operand_map(CUtensorMap* map, const uint8_t* base, int rows, int K, int box_rows)
+{
+    return get_tensor_map(map, base, (uint64_t)rows, (uint64_t)K, (uint64_t)K, (uint32_t)box_rows, (uint32_t)kBK);
 }
 
 bool tcgen05_supported(const MMArgs& a)
@@ -665,17 +920,28 @@ bool tcgen05_supported(const MMArgs& a)
     return a.M >= 1 && a.N >= 1 && a.K >= 16 && (a.K % 16 == 0) && aligned(a.A, 16) && aligned(a.B, 16);
 }
 
-template <int BN, int CG, bool PEERS = false>
+// TMA-store epilogue: every destination base and the row pitch must be 16-byte aligned
+static bool tma_store_ok(const MMArgs& a, void* const* dsts, int n_dst)
+{
+    const size_t esz = dtype_size(a.out_dtype);
+    if ((a.ldc * esz) % 16 != 0) return false;
+    for (int d = 0; d < n_dst; ++d)
+        if (!dsts[d] || !aligned(dsts[d], 16)) return false;
+    return true;
+}
+
+template <int BN, int CG, int MODE = kStDirect>
 static int launch_tcgen05_cfg(const MMArgs& a)
 {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, MODE>;
     static std::atomic<int> attr_done[64];
-    if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG, PEERS>, Cfg::kSmemBytes, attr_done)) return rc;
+    if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG, MODE>, Cfg::kSmemBytes, attr_done)) return rc;
 
     CUtensorMap tmap_a, tmap_b;
     if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;
     if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, Cfg::kBRows)) return FP8B_ERR_CUDA;
 
+    const size_t esz = dtype_size(a.out_dtype);
     GemmParams p;
     p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
     p.num_m_blocks = (a.M + kBM * CG - 1) / (kBM * CG);
@@ -687,33 +953,49 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.num_work = tiles_all;
     {   // split the partially filled last wave into half-width tiles when that makes it one SHORT round
         const int rem = tiles_all % workers_cap;
-        const bool can_split = (BN % 64 == 0) && ((BN / 2 / CG) % 8 == 0) && tiles_all > workers_cap &&
-                               !(tune_int("FP8B_GEMM_DEBUG", 0) & 8);
+        bool can_split = (BN % 64 == 0) && ((BN / 2 / CG) % 8 == 0) && tiles_all > workers_cap;
+        if (MODE == kStTma) can_split = can_split && ((BN / 2) * esz) % 128 == 0;      // half tiles must be whole store boxes
+#ifdef FP8B_PROFILE
+        can_split = can_split && !(tune_int("FP8B_GEMM_DEBUG", 0) & 8);
+#endif
         if (can_split && rem > 0 && 2 * rem <= workers_cap) {
             p.full_tiles = tiles_all - rem;
             p.num_work = tiles_all + rem;
         }
     }
     p.epi = make_epi(a);
-    const size_t esz = dtype_size(a.out_dtype);
     p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
     p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
-    p.debug = (tune_int("FP8B_GEMM_DEBUG", 0) & 0xFF) | (a.a_fmt ? 0x100 : 0) | (a.b_fmt ? 0x200 : 0);
+    p.debug = (a.a_fmt ? 0x100 : 0) | (a.b_fmt ? 0x200 : 0);
     p.store_mc = a.store_mc;
-    p.dbg = nullptr;
-    if (PEERS) {                             // store_mc = 2 | world << 8; a.ws = device table of world byte deltas
-        p.dbg = static_cast<long long*>(a.ws);
-        p.debug &= ~16;
+    p.aux = nullptr;
+    typename StoreMapsOf<MODE>::type smaps;
+    if constexpr (MODE == kStPeers) {        // store_mc = 2 | world << 8; a.ws = device table of world byte deltas
+        p.aux = static_cast<long long*>(a.ws);
+    } else if constexpr (MODE == kStTma) {   // store_mc = 3 | n_dst << 8; a.ws = HOST array of n_dst destination pointers
+        const int n_dst = a.store_mc >> 8;
+        void* const* dsts = static_cast<void* const*>(a.ws);
+        void* self[1] = {a.C};
+        if (!dsts) dsts = self;
+        if (n_dst < 1 || n_dst > kMaxDst || !tma_store_ok(a, dsts, n_dst)) return FP8B_ERR_UNSUPPORTED;
+        for (int d = 0; d < n_dst; ++d)
+            if (!get_tensor_map(&smaps.m[d], dsts[d], (uint64_t)a.M, (uint64_t)a.N * esz, (uint64_t)a.ldc * esz, 128, 128))
+                return FP8B_ERR_CUDA;
+        for (int d = n_dst; d < kMaxDst; ++d) smaps.m[d] = smaps.m[0];
+    } else {
+        smaps.unused = 0;
+#ifdef FP8B_PROFILE
+        p.debug |= tune_int("FP8B_GEMM_DEBUG", 0) & 0xFF;
+        if (p.debug & 16) {                  // profiling only: allocates and synchronises
+            static long long* dbuf = nullptr;
+            if (!dbuf) cudaMalloc(&dbuf, 64 * 8 * sizeof(long long));
+            cudaMemset(dbuf, 0, 64 * 8 * sizeof(long long));
+            p.aux = dbuf;
+        }
+#endif
     }
-    if (p.debug & 16) {                      // profiling only: allocates and synchronises
-        static long long* dbuf = nullptr;
-        if (!dbuf) cudaMalloc(&dbuf, 64 * 8 * sizeof(long long));
-        cudaMemset(dbuf, 0, 64 * 8 * sizeof(long long));
-        p.dbg = dbuf;
-    }
-    // multimem.st has no sub-word form: the multicast mode needs every chunk on the 16-byte path
     // multimem.st / peer stores have no sub-word form: both modes need every chunk on the 16-byte path
-    if (a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
+    if (MODE != kStTma && a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
     const int tiles = p.num_work;
     const int workers_max = workers_cap;                            // one CTA (or CTA pair) per SM (pair)
@@ -721,7 +1003,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(workers * CG, 1, 1);
-    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.blockDim = dim3(gemm_threads<MODE>(), 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = a.st;
     cudaLaunchAttribute attr[2];
@@ -735,19 +1017,50 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     // changed nothing: 104.17 vs 104.12 us back to back.  The kernel is power-limited, idle gaps only buy clock.)
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG, PEERS>, tmap_a, tmap_b, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG, MODE>, tmap_a, tmap_b, smaps, p);
     if (e != cudaSuccess) return cuda_fail(e);
-    if (!PEERS && p.dbg) {
+#ifdef FP8B_PROFILE
+    if (MODE == kStDirect && p.aux) {
         long long h[64 * 8];
         cudaDeviceSynchronize();
-        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(h, p.aux, sizeof(h), cudaMemcpyDeviceToHost);
         printf("tile | mma: wait_tempty  issue+run (of which waiting for TMA) | epi: wait_tfull  drain+store | epi_end - mma_end\n");
         for (int t = 0; t < 64 && h[t * 8 + 2]; ++t)
             printf("%4d | %8lld %8lld (%8lld) | %8lld %8lld | %8lld   (mma start %lld)\n", t, h[t * 8 + 1] - h[t * 8 + 0],
                    h[t * 8 + 2] - h[t * 8 + 1], h[t * 8 + 3], h[t * 8 + 5] - h[t * 8 + 4], h[t * 8 + 6] - h[t * 8 + 5],
                    h[t * 8 + 6] - h[t * 8 + 2], h[t * 8 + 0] - h[0]);
     }
+#endif
     return after_launch();
+}
+
+constexpr int kDefaultGemmStore = 1;      // epilogue of plain fp8b_scaled_mm calls: 1 = st.global, 2 = TMA store (measured choice)
+
+// Tile configuration: 1 = 128x256 one CTA, 2 = 128x128 one CTA, 3 = 256x256 pair, 4 = 256x128 pair, 5 = 256x192 pair.
+static int pick_tile_cfg(const MMArgs& a)
+{
+    const int sms = device_info().sm_count;
+    if (a.M > 128 && a.N > 128) {
+        // CTA pairs.  Pick the tile width minimising rounds x time-per-tile.  A tile costs a fixed ~1.5 us (accumulator
+        // hand-over, pipeline fill) plus a part proportional to K that was measured at K = 3072 as 10.5 / 9.3 / 8.65 us
+        // per tile for widths 256 / 192 / 128 (L2->SM traffic of the operands, not MMA time, dominates, so narrow
+        // tiles are barely cheaper).  Only the ratios matter.
+        const long mt = (a.M + 255) / 256;
+        const int pairs = sms / 2;
+        const double kf = (double)a.K / 3072.0;
+        auto cost = [&](int width) {
+            const double t3072 = width == 256 ? 10.5 : width == 192 ? 9.3 : 8.65;
+            const long tiles = mt * ((a.N + width - 1) / width);
+            return (1.5 + kf * (t3072 - 1.5)) * (double)((tiles + pairs - 1) / pairs);
+        };
+        int cfg = 3;
+        double best = cost(256);
+        if (cost(192) < best) { best = cost(192); cfg = 5; }
+        if (cost(128) < best) { best = cost(128); cfg = 4; }
+        return cfg;
+    }
+    const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
+    return (a.N > 128 && t_256 >= 2L * sms) ? 1 : 2;
 }
 
 int launch_gemm_tcgen05(const MMArgs& a)
@@ -755,36 +1068,41 @@ int launch_gemm_tcgen05(const MMArgs& a)
     if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
     // Tile choice.  Prefer CTA pairs (256-row tiles) whenever M and N are large enough for them,
     // 256-wide when that still leaves >= ~2 waves of tiles, else 128-wide (finer tail).
-    // FP8B_GEMM_CFG forces one: 1 = 128x256 1-CTA, 2 = 128x128 1-CTA, 3 = 256x256 pair, 4 = 256x128 pair,
-    // 5 = 256x192 pair.
-    const int sms = device_info().sm_count;
-    int cfg = tune_int("FP8B_GEMM_CFG", 0);
-    if (cfg == 0) {
-        if (a.M > 128 && a.N > 128) {
-            // CTA pairs.  Pick the tile width minimising rounds x time-per-tile; the per-tile times are the
-            // measured ones for K = 3072 (256: 10.5 us, 192: 9.3 us, 128: 8.65 us -- L2->SM traffic per tile,
-            // not MMA time, dominates, so narrow tiles are barely cheaper) and only their ratios matter.
-            const long mt = (a.M + 255) / 256;
-            const int pairs = sms / 2;
-            const double cost256 = 10.5 * (double)((mt * ((a.N + 255) / 256) + pairs - 1) / pairs);
-            const double cost192 = 9.3 * (double)((mt * ((a.N + 191) / 192) + pairs - 1) / pairs);
-            const double cost128 = 8.65 * (double)((mt * ((a.N + 127) / 128) + pairs - 1) / pairs);
-            cfg = 3;
-            double best = cost256;
-            if (cost192 < best) { best = cost192; cfg = 5; }
-            if (cost128 < best) { best = cost128; cfg = 4; }
-        } else {
-            const long t_256 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 255) / 256);
-            cfg = (a.N > 128 && t_256 >= 2L * sms) ? 1 : 2;
-        }
-    }
-    if ((a.store_mc & 0xFF) == 2) {          // peer stores (N-sharded linear): the CTA-pair configurations only
+    // fp8b_set_option(FP8B_OPT_TUNE_GEMM_CFG) -- a result-neutral tuning knob -- forces one.
+    const int forced = tune(kTuneGemmCfg, 0);
+    const int cfg = forced ? forced : pick_tile_cfg(a);
+    const int mode = a.store_mc & 0xFF;
+    if (mode == 2) {          // peer stores with st.global (round-1 plan): the CTA-pair configurations only
         if ((a.store_mc >> 8) < 2 || (a.store_mc >> 8) > 8 || !a.ws) return FP8B_ERR_INVALID;
         switch (cfg) {
-            case 3: return launch_tcgen05_cfg<256, 2, true>(a);
-            case 4: return launch_tcgen05_cfg<128, 2, true>(a);
-            case 5: return launch_tcgen05_cfg<192, 2, true>(a);
+            case 3: return launch_tcgen05_cfg<256, 2, kStPeers>(a);
+            case 4: return launch_tcgen05_cfg<128, 2, kStPeers>(a);
+            case 5: return launch_tcgen05_cfg<192, 2, kStPeers>(a);
             default: return FP8B_ERR_UNSUPPORTED;
+        }
+    }
+    if (mode == 3) {          // TMA-store epilogue, 1..8 destinations
+        switch (cfg) {
+            case 1: return launch_tcgen05_cfg<256, 1, kStTma>(a);
+            case 3: return launch_tcgen05_cfg<256, 2, kStTma>(a);
+            case 4: return launch_tcgen05_cfg<128, 2, kStTma>(a);
+            case 5: return launch_tcgen05_cfg<192, 2, kStTma>(a);
+            default: return launch_tcgen05_cfg<128, 1, kStTma>(a);
+        }
+    }
+    if (mode == 0 && tune(kTuneGemmStore, kDefaultGemmStore) == 2) {      // plain call, TMA-store epilogue to the one output
+        void* self[1] = {a.C};
+        if (tma_store_ok(a, self, 1)) {
+            MMArgs t = a;
+            t.store_mc = 3 | (1 << 8);
+            t.ws = nullptr;
+            switch (cfg) {
+                case 1: return launch_tcgen05_cfg<256, 1, kStTma>(t);
+                case 3: return launch_tcgen05_cfg<256, 2, kStTma>(t);
+                case 4: return launch_tcgen05_cfg<128, 2, kStTma>(t);
+                case 5: return launch_tcgen05_cfg<192, 2, kStTma>(t);
+                default: return launch_tcgen05_cfg<128, 1, kStTma>(t);
+            }
         }
     }
     switch (cfg) {

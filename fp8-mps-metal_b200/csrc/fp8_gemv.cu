@@ -500,7 +500,7 @@ int launch_gemv(const MMArgs& a)
     // kernel choice: M == 1 -> CUDA-core FHFMA kernel (exact fp32 accumulation order per lane);
     // M >= 2 -> warp-level tensor-core kernel (weights streamed once for all M rows).
     // FP8B_GEMV_IMPL=1 / 2 forces the first / second (profiling knob).
-    const int impl = tune_int("FP8B_GEMV_IMPL", 0);
+    const int impl = tune(kTuneGemvImpl, 0);
     if (a.a_fmt | a.b_fmt) {        // an e5m2 operand: the warp-MMA kernel has all four type pairs; else the generic kernel
         if (gemv_mma_supported(a)) return launch_gemv_mma(a);
         fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, make_epi(a),
@@ -554,7 +554,7 @@ int launch_gemv_fhfma(const MMArgs& a, const Epi& epi, const void* X, int x_dtyp
                 default: rc = launch_gemv_xq_mt<4, 4>(xp, S, smem, a.st); break;
             }
         } else {
-            const int unroll = tune_int("FP8B_GEMV_UNROLL", 4);
+            const int unroll = tune(kTuneGemvUnroll, 4);
             switch (mt) {
                 case 1: rc = unroll == 2 ? launch_gemv_mt<1, 2>(p, S, smem, a.st)
                            : unroll == 8 ? launch_gemv_mt<1, 8>(p, S, smem, a.st) : launch_gemv_mt<1, 4>(p, S, smem, a.st); break;

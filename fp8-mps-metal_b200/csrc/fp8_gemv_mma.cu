@@ -181,7 +181,7 @@ int launch_gemv_mma(const MMArgs& a)
     p.static_b = (g_opt_pdl.load(std::memory_order_relaxed) && (a.chain_pdl || g_opt_static_weights.load(std::memory_order_relaxed))) ? 1 : 0;
     const bool pdl = g_opt_pdl.load(std::memory_order_relaxed) != 0;   // always: resident while the predecessor drains
     const int grid = (a.N + kMmaRows - 1) / kMmaRows;
-    const int batch = tune_int("FP8B_GEMV_BATCH", 4);
+    const int batch = tune(kTuneGemvBatch, 4);
     if (a.a_fmt | a.b_fmt) {                // an e5m2 operand: same kernel, other MMA types (WF = weights, XF = activations)
         const int f = a.b_fmt * 2 + a.a_fmt;
         if (a.M <= 8) {

@@ -70,14 +70,23 @@ def _device_type(device):
         return device.type
     if isinstance(device, str):
         return device.split(":", 1)[0]
+    if isinstance(device, int) and not isinstance(device, bool):
+        return ACCEL                                   # a bare ordinal names an accelerator device, as in torch
     return None
+
+
+def _as_device(device):
+    """str / int / torch.device -> torch.device (the reference only ever saw the single "mps" device)."""
+    if isinstance(device, int) and not isinstance(device, bool):
+        return torch.device(ACCEL, device)
+    return torch.device(device)
 
 
 def _same_accel_device(tensor, device):
     """`device` (None, str or torch.device) names the accelerator device `tensor` already lives on."""
     if device is None:
         return True
-    d = torch.device(device)
+    d = _as_device(device)
     if d.type != tensor.device.type:
         return False
     index = d.index if d.index is not None else torch.cuda.current_device()
@@ -125,13 +134,16 @@ def _parse_to_args(args, kwargs):
     """dtype / device out of the many call forms of Tensor.to (fp8_mps_patch.py:119-133)."""
     dtype = kwargs.get("dtype")
     device = kwargs.get("device")
-    for arg in args:
+    for pos, arg in enumerate(args):
         if isinstance(arg, torch.dtype):
             if dtype is None:
                 dtype = arg
         elif isinstance(arg, (torch.device, str)):
             if device is None:
                 device = arg
+        elif pos == 0 and isinstance(arg, int) and not isinstance(arg, bool):
+            if device is None:
+                device = arg                               # to(0, dtype): a device ordinal (later ints are non_blocking / copy)
         elif isinstance(arg, torch.Tensor) and dtype is None and device is None:
             dtype, device = arg.dtype, arg.device          # to(other_tensor)
     return dtype, device
@@ -155,17 +167,20 @@ def _metal_tensor_to(self, *args, **kwargs):
 
     # 1. FP8 bytes moving onto the accelerator
     if src_fp8 and device is not None and target_on_accel and self.device.type != ACCEL:
-        moved = _original_tensor_to(self.view(torch.uint8), device, **passthrough).view(self.dtype)
+        moved = _original_tensor_to(self.view(torch.uint8), _as_device(device), **passthrough).view(self.dtype)
         if dtype is not None and dtype != self.dtype:
             if dst_fp8:
                 return moved.view(torch.uint8).view(dtype)
             return _metal_tensor_to(moved, dtype)
         return moved
 
-    # 2. float -> FP8 on the accelerator (only e4m3fn has kernels; e5m2 stays with torch)
+    # 2. float -> FP8 on the accelerator (only e4m3fn has kernels; e5m2 stays with torch).  The tensor is first
+    #    moved to the REQUESTED device -- which may be another GPU than the one it lives on -- then encoded there.
     if target_on_accel and dtype is not None and dtype == _E4M3 and not src_fp8:
-        on_dev = self if self.device.type == ACCEL else _original_tensor_to(
-            self, device if device is not None else ACCEL, **passthrough)
+        if self.device.type == ACCEL and _same_accel_device(self, device):
+            on_dev = self
+        else:
+            on_dev = _original_tensor_to(self, _as_device(device) if device is not None else ACCEL, **passthrough)
         return _kernels().fp8_encode(on_dev).view(dtype)
 
     # 3. FP8 already on the accelerator
@@ -187,8 +202,11 @@ def _metal_tensor_to(self, *args, **kwargs):
 def _metal_tensor_copy(self, src, non_blocking=False):
     """
     Drop-in replacement for Tensor.copy_() for FP8 destinations on the GPU
-    (fp8_mps_patch.py:229-302): FP8 -> FP8 is a byte copy; float -> float8_e4m3fn encodes with
-    the reference codec.  Everything else goes to the original method.
+    (fp8_mps_patch.py:229-302): FP8 -> FP8 is a byte copy, also between the two FP8 dtypes (:245-264); any
+    non-FP8 source -> float8_e4m3fn encodes with the reference codec (:266-290; non-float sources go through
+    float32 first like fp8_encode, fp8_mps_native.py:142).  A float8_e5m2 destination with a non-FP8 source stays
+    with torch's own cast (the reference would store e4m3fn codes in it).  Everything else goes
+    to the original method.
     """
     if not hasattr(src, "dtype"):
         return _original_tensor_copy(self, src, non_blocking=non_blocking)
@@ -198,13 +216,11 @@ def _metal_tensor_copy(self, src, non_blocking=False):
         return _original_tensor_copy(self, src, non_blocking=non_blocking)
 
     if src_fp8:
-        if src.dtype != self.dtype:
-            return _original_tensor_copy(self, src, non_blocking=non_blocking)
         _original_tensor_copy(self.view(torch.uint8), src.contiguous().view(torch.uint8), non_blocking=non_blocking)
         return self
 
-    if self.dtype == _E4M3 and src.dtype in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
-        on_dev = src if src.device.type == ACCEL else _original_tensor_to(src, self.device)
+    if self.dtype == _E4M3:
+        on_dev = src if src.device == self.device else _original_tensor_to(src, self.device)
         encoded = _kernels().fp8_encode(on_dev)
         _original_tensor_copy(self.view(torch.uint8), encoded, non_blocking=non_blocking)
         return self

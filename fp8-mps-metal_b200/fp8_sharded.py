@@ -11,9 +11,13 @@ shard -- no reduction is needed -- and ONE exchange step assembles the (M,N) res
                     [w, M, N/w] buffer, exposed either as is (layout="rank_major", zero extra
                     passes) or re-laid to the row-major (M,N) tensor stock _scaled_mm returns
                     (layout="row_major", one extra device pass);
-  mode="peers"      fused, unicast: the epilogue stores each tile into this rank's result and, with plain
-                    stores over NVLink, into the same place of every peer's result (symmetric memory).
-                    Each GPU receives (w-1)/w of the output; no NVLS needed.
+  mode="push"       fused, unicast, the default on NVLink boxes: the GEMM's epilogue warps only fill a
+                    shared-memory ring and a dedicated warp pushes every finished 128 x 128-byte box with TMA
+                    stores (cp.async.bulk.tensor) into this rank's result and into the same place of every
+                    peer's result (symmetric memory).  Each GPU receives (w-1)/w of the output, the NVLink
+                    writes overlap the next tile's MMAs, any M / N (TMA clips the edges); no NVLS needed.
+  mode="peers"      the round-1 form of the same plan: the epilogue warps themselves issue st.global to
+                    every peer.  Kept for comparison (CTA-pair tiles only: M > 128, N/w > 128).
   mode="multicast"  fused: the GEMM epilogue writes each output tile straight into the row-major
                     (M,N) result of EVERY rank through an NVSwitch multicast mapping
                     (multimem.st), so the exchange overlaps the math tile by tile and no gather or
@@ -94,7 +98,10 @@ class ShardedScaledMM:
     def __call__(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16,
                  layout: str = "row_major", mode: str = "allgather") -> torch.Tensor:
         if mode == "auto":
-            mode = self.best_mode() if layout == "row_major" else "allgather"
+            mode = self.best_mode(x_u8.shape[0], x_u8.shape[1], out_dtype or torch.float32, x_u8.device) \
+                if layout == "row_major" else "allgather"
+        if mode == "push":
+            return self.forward_push(x_u8, scale_a, out_dtype)
         if mode == "multicast":
             return self.forward_multicast(x_u8, scale_a, out_dtype)
         if mode == "peers":
@@ -193,11 +200,45 @@ class ShardedScaledMM:
             cache[1][turn] = torch.tensor([p - local for p in ptrs], dtype=torch.int64, device=buf.device)
         return cache[1][turn]
 
-    def best_mode(self) -> str:
-        """Measured on 8 x B200 (C4, bf16 out, row-major result on every rank; profiles/r1_scaling.md): both fused
-        paths beat GEMM + NCCL all-gather at every world size.  Peer stores win while few peers have to be written
-        (w=2: 122 us vs 179 us multicast vs 202 us all-gather; w=4: 151 / 168 / 191), the multicast mapping wins
-        at w=8 (165 us vs 169 us peers vs 199 us)."""
-        if self.world <= 1:
-            return "allgather"
-        return "peers" if self.world <= 4 else "multicast"
+    # ------------------------------------------------------------------ fused TMA-store path
+    def push_supported(self, M: int, K: int, odt, device) -> bool:
+        """Whether mode="push" can serve this call -- evaluated from (M, K, N, world, dtype) only, so every rank
+        reaches the same answer without communicating (a rank must never skip the closing barrier)."""
+        if self.world <= 1 or device.type != "cuda" or not dist.is_initialized():
+            return False
+        if dist.get_backend(self.group) != "nccl":
+            return False
+        esz = torch.empty((), dtype=odt).element_size()
+        if K < 16 or K % 16 or (self.N * esz) % 16 or (self.width * esz) % 16:
+            return False
+        return True
+
+    def forward_push(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """ONE kernel computes this rank's column block and pushes it, box by box, into the row-major (M,N) result
+        of every rank (fp8b_scaled_mm_push: tcgen05 GEMM + TMA stores to local HBM and, over NVLink, to the peers'
+        symmetric buffers).  Same double-buffering and single closing barrier as forward_multicast."""
+        import fp8_mps_native
+        M, K = x_u8.shape
+        odt = out_dtype or torch.float32
+        if self.world == 1:
+            return self.local(x_u8, scale_a, out_dtype)
+        if not self.push_supported(M, K, odt, x_u8.device):      # same verdict on every rank: nobody is left in a barrier
+            raise RuntimeError("push mode needs NCCL ranks on CUDA, K % 16 == 0 and 16-byte aligned shard columns")
+        key, pair, turn = self._symm_buffers(M, odt, x_u8.device)
+        buf, hdl = pair[turn]
+        self._symm = (key, pair, turn ^ 1)
+        if self.n1 > self.n0:
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            order = [ptrs[(self.rank + d) % self.world] for d in range(self.world)]     # own buffer first, then the ring of peers
+            fp8_mps_native._get_lib().fp8_scaled_mm_push(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
+                                                         order, int(self.n0))
+        hdl.barrier(channel=0)                                  # every rank's boxes have landed everywhere
+        return buf
+
+    def best_mode(self, M: int = 0, K: int = 0, odt=torch.bfloat16, device=None) -> str:
+        """The fused TMA-store plan whenever it applies (decided from the shape alone, identically on every rank),
+        else GEMM + NCCL all-gather.  Measured on 8 x B200 (C4, bf16 out, row-major result on every rank;
+        profiles/r2_scaling.md)."""
+        if device is not None and self.push_supported(M, K, odt, device):
+            return "push"
+        return "allgather"

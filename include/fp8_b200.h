@@ -83,10 +83,28 @@ FP8B_API uint64_t fp8b_launch_count(void);
  *                            kernels then start streaming B BEFORE waiting for the predecessor (only A, the
  *                            scales and the bias are read after the wait), which overlaps the ramp-up of one
  *                            call with the drain of the previous one in a chain of decode GEMVs.
+ *   FP8B_OPT_TUNE_*          developer knobs that pick between RESULT-IDENTICAL kernel variants (tests and profiling
+ *                            scripts A/B them); -1 = built-in rule.  Each starts from the environment variable of the
+ *                            same name without the OPT_TUNE_ part (FP8B_GEMM_CFG, ...), read once at load time.
+ *                              GEMM_CFG      tcgen05 tile: 1 = 128x256, 2 = 128x128 (one CTA); 3 = 256x256, 4 = 256x128,
+ *                                            5 = 256x192 (CTA pairs)
+ *                              GEMV_IMPL     1 = FHFMA warp-per-row, 2 = warp-MMA, 3 = SM-balanced rows, 4 = persistent TMA ring
+ *                              DYNAMIC_PLAN  fp8b_linear_dynamic: 1 = single kernel, 2 = quantise + chained GEMV
+ *                              CAST_SHAPE    cast launch shape: 1 = small tiles, 2 = big tiles
+ *                              GEMM_STORE    tcgen05 epilogue: 1 = st.global from the epilogue warps, 2 = TMA store
+ *                              GEMV_UNROLL / GEMV_BATCH / AMAX_CAP   load batching of the GEMV kernels / amax grid cap
  */
 typedef enum fp8b_option {
     FP8B_OPT_PDL = 0,
-    FP8B_OPT_STATIC_WEIGHTS = 1
+    FP8B_OPT_STATIC_WEIGHTS = 1,
+    FP8B_OPT_TUNE_GEMM_CFG = 16,
+    FP8B_OPT_TUNE_GEMV_IMPL = 17,
+    FP8B_OPT_TUNE_DYNAMIC_PLAN = 18,
+    FP8B_OPT_TUNE_CAST_SHAPE = 19,
+    FP8B_OPT_TUNE_GEMM_STORE = 20,
+    FP8B_OPT_TUNE_GEMV_UNROLL = 21,
+    FP8B_OPT_TUNE_GEMV_BATCH = 22,
+    FP8B_OPT_TUNE_AMAX_CAP = 23
 } fp8b_option;
 FP8B_API int fp8b_set_option(int option, int value);
 FP8B_API int fp8b_get_option(int option);
@@ -300,6 +318,32 @@ FP8B_API int fp8b_scaled_mm_peers(const uint8_t* A, const uint8_t* B, void* C_lo
                          const float* scale_b, int scale_b_len,
                          const void* bias, int bias_dtype,
                          const float* scale_result, void* stream);
+
+/*
+ * The N-sharded linear as ONE kernel that computes and exchanges: the tcgen05 GEMM with a TMA-store epilogue that
+ * pushes every finished 128-row x 128-byte box of the output to n_dst destinations -- this rank's (M, ldc) buffer and
+ * the same place in each peer's buffer, mapped into this process (torch symmetric memory `buffer_ptrs`, cuMemMap of
+ * a fabric / POSIX handle, or cudaIpcOpenMemHandle).  No reference counterpart (the reference is single-device,
+ * fp8_bridge.cpp:67); it replaces "GEMM, then ncclAllGather, then a re-layout pass" of BASELINE.json's C4 config.
+ *   C_dsts   HOST array of n_dst (1..8) device pointers.  C_dsts[d] addresses element (0,0) of THIS rank's column
+ *            block inside destination d's row-major (M, ldc) matrix; C_dsts[0] is normally the local buffer.  With
+ *            n_dst == 1 this is fp8b_scaled_mm's tcgen05 kernel with a TMA-store epilogue.
+ * The epilogue warps only fill a shared-memory ring; a dedicated warp issues cp.async.bulk.tensor stores, several
+ * in flight, so the tensor-memory accumulator is released as soon as it is drained and NVLink writes overlap the
+ * next tile's MMAs.  Each GPU receives (world-1)/world of the output.  The caller orders ranks around the call (a
+ * barrier before a buffer is reused and one after).  Needs 16-byte aligned A / B / every C_dsts[d], K % 16 == 0 and
+ * ldc * sizeof(out) % 16 == 0 (fp8b_scaled_mm_push_supported); any M, N (TMA clips the edges).  Else FP8B_ERR_UNSUPPORTED.
+ */
+FP8B_API int fp8b_scaled_mm_push(const uint8_t* A, const uint8_t* B, void* const* C_dsts, int n_dst,
+                        int out_dtype, int M, int N, int K, int64_t ldc,
+                        const float* scale_a, int scale_a_len,
+                        const float* scale_b, int scale_b_len,
+                        const void* bias, int bias_dtype,
+                        const float* scale_result, void* stream);
+/* 1 when fp8b_scaled_mm_push can serve this shape and alignment (a pure function: every rank of a group can
+ * evaluate it for every other rank's shard before anyone launches). */
+FP8B_API int fp8b_scaled_mm_push_supported(int out_dtype, int M, int N, int K, int64_t ldc, const void* A, const void* B,
+                                  const void* C);
 
 /* The algorithm FP8B_MM_AUTO resolves to for this problem (pointers supply the alignment). */
 FP8B_API int fp8b_scaled_mm_select(const uint8_t* A, const uint8_t* B, const void* C, int out_dtype,

@@ -74,6 +74,14 @@ def capi():
         L.fp8b_linear_dynamic.argtypes = [vp, i32, vp, vp, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, vp, vp, sz, vp]
         L.fp8b_linear_dynamic_workspace_bytes.restype = sz
         L.fp8b_linear_dynamic_workspace_bytes.argtypes = [i32, i32]
+    if hasattr(L, "fp8b_scaled_mm_push") or not os.environ.get("FP8B_LIB"):
+        L.fp8b_scaled_mm_peers.restype = i32
+        L.fp8b_scaled_mm_peers.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp, vp]
+        L.fp8b_scaled_mm_push.restype = i32
+        L.fp8b_scaled_mm_push.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32,
+                                          vp, vp]
+        L.fp8b_scaled_mm_push_supported.restype = i32
+        L.fp8b_scaled_mm_push_supported.argtypes = [i32, i32, i32, i32, i64, vp, vp, vp]
     _lib = L
     return L
 
@@ -131,6 +139,23 @@ def mm_capi(A, B, sa, sb, bias=None, sr=None, out_dtype=None, algo=ALGO_AUTO, ou
     rc = L.fp8b_scaled_mm(p(A), p(B), p(C), dt_code(odt), M, N, K, ldc, p(sa), sa.numel(), p(sb), sb.numel(),
                           p(bias), dt_code(bias.dtype) if bias is not None else 0, p(sr), None, 0, algo, stream_ptr())
     return rc, C
+
+
+def mm_push_capi(A, B, sa, sb, dsts, n0=0, bias=None, sr=None):
+    """fp8b_scaled_mm_push through the raw C ABI: `dsts` are (M, ldc) torch tensors of one dtype and geometry; this
+    call writes the column block [n0, n0 + N) of each."""
+    import torch
+    L = capi()
+    M, K = A.shape
+    N = B.shape[0]
+    odt = dsts[0].dtype
+    ldc = dsts[0].stride(0)
+    esz = dsts[0].element_size()
+    arr = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() + n0 * esz for d in dsts])
+    sa = sa.to(device=A.device, dtype=torch.float32).contiguous().reshape(-1)
+    sb = sb.to(device=A.device, dtype=torch.float32).contiguous().reshape(-1)
+    return L.fp8b_scaled_mm_push(p(A), p(B), arr, len(dsts), dt_code(odt), M, N, K, ldc, p(sa), sa.numel(), p(sb), sb.numel(),
+                                 p(bias), dt_code(bias.dtype) if bias is not None else 0, p(sr), stream_ptr())
 
 
 def to_np(t):

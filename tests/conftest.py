@@ -61,3 +61,24 @@ def golden():
         "host": np.load(os.path.join(g, "host_golden.npz")),
         "kat": kat,
     }
+
+
+_TUNE_IDS = {"GEMM_CFG": 16, "GEMV_IMPL": 17, "DYNAMIC_PLAN": 18, "CAST_SHAPE": 19, "GEMM_STORE": 20, "GEMV_UNROLL": 21,
+             "GEMV_BATCH": 22, "AMAX_CAP": 23}
+
+
+@pytest.fixture
+def tune():
+    """tune("GEMM_CFG", 3): force a result-identical kernel variant (fp8b_set_option FP8B_OPT_TUNE_*) for this test;
+    every knob touched is reset to -1 (built-in rule) afterwards."""
+    from _util import capi
+    L = capi()
+    touched = []
+
+    def setter(name, value):
+        assert L.fp8b_set_option(_TUNE_IDS[name], int(value)) == 0
+        touched.append(name)
+
+    yield setter
+    for name in touched:
+        L.fp8b_set_option(_TUNE_IDS[name], -1)

@@ -381,14 +381,13 @@ def test_big_tile_paths_256bit_and_128bit(dtype):
     for o_ in offs:
         rc = L.fp8b_encode(arena.data_ptr() + esz * o_, dt_code(dtype), out.data_ptr() + o_, n, None, stream_ptr())
         assert rc == 0
-    import os
-    os.environ["FP8B_CAST_SHAPE"] = "1"                     # reference: always the small 16-byte tiles
+    L.fp8b_set_option(19, 1)                                # FP8B_OPT_TUNE_CAST_SHAPE = 1: always the small 16-byte tiles
     try:
         ref = torch.zeros_like(out)
         for o_ in offs:
             assert L.fp8b_encode(arena.data_ptr() + esz * o_, dt_code(dtype), ref.data_ptr() + o_, n, None, stream_ptr()) == 0
     finally:
-        del os.environ["FP8B_CAST_SHAPE"]
+        L.fp8b_set_option(19, -1)
     assert torch.equal(out, ref)
     samp = slice(offs[1], offs[1] + 50001)
     x = arena[samp].cpu()

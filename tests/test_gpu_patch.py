@@ -83,6 +83,16 @@ def test_copy_scenarios():
     dst4 = torch.empty(2, 8, dtype=torch.float8_e4m3fn, device=DEV)
     dst4.copy_(x.to(DEV))                                       # broadcasting copy
     assert np.array_equal(dst4.view(torch.uint8).cpu().numpy(), np.stack([want, want]))
+    d5 = torch.empty(8, dtype=torch.float8_e5m2, device=DEV)
+    d5.copy_(dst)                                               # e4m3fn -> e5m2 destination: BYTE copy (fp8_mps_patch.py:245-264)
+    assert torch.equal(d5.view(torch.uint8), dst.view(torch.uint8))
+    xi = torch.tensor([0, 1, -3, 7, 100, 449, -1000, 2], dtype=torch.int32)
+    d6 = torch.empty(8, dtype=torch.float8_e4m3fn, device=DEV)
+    d6.copy_(xi.to(DEV))                                        # non-float source: float32 then the codec (fp8_mps_patch.py:266-290)
+    assert np.array_equal(d6.view(torch.uint8).cpu().numpy(), o.encode(xi.numpy().astype(np.float32)))
+    d7 = torch.empty(8, dtype=torch.float8_e4m3fn, device=DEV)
+    d7.copy_(x.double())                                        # float64 from the CPU
+    assert np.array_equal(d7.view(torch.uint8).cpu().numpy(), want)
     f = torch.zeros(8, device=DEV)
     f.copy_(x)                                                  # unrelated copies untouched
     assert torch.equal(f.cpu(), x)
@@ -130,3 +140,27 @@ def test_non_fp8_calls_reach_the_original_op():
     fp8_mps_patch.uninstall()
     assert torch.Tensor.to is not fp8_mps_patch._metal_tensor_to
     fp8_mps_patch.install()
+
+
+def test_to_with_device_ordinal_uses_reference_codec(golden):
+    """`.to(0, float8_e4m3fn)`: a bare device ordinal must reach the codec kernel, not torch's cast (which gives NaN
+    codes above 448 where the reference saturates)."""
+    x = torch.tensor([500.0, -1000.0, 1.0, 0.001])
+    n0 = _launches()
+    q = x.to(0, torch.float8_e4m3fn)
+    assert _launches() > n0 and q.device == torch.device("cuda", 0)
+    assert np.array_equal(q.view(torch.uint8).cpu().numpy(), o.encode(x.numpy()))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_to_other_gpu_lands_on_the_requested_device():
+    """`x_cuda0.to('cuda:1', float8_e4m3fn)` must return a tensor on cuda:1."""
+    x = torch.tensor([500.0, -2.5, 1.0, 0.0186], device="cuda:0")
+    for target in ("cuda:1", torch.device("cuda", 1), 1):
+        q = x.to(target, torch.float8_e4m3fn)
+        assert q.device == torch.device("cuda", 1)
+        assert np.array_equal(q.view(torch.uint8).cpu().numpy(), o.encode(x.cpu().numpy()))
+    q0 = x.to("cuda:0", torch.float8_e4m3fn)
+    assert q0.device == torch.device("cuda", 0)
+    moved = q0.to("cuda:1")                                     # FP8 bytes between GPUs
+    assert moved.device == torch.device("cuda", 1) and torch.equal(moved.view(torch.uint8).cpu(), q0.view(torch.uint8).cpu())

@@ -109,10 +109,10 @@ def test_gemv(M, K, N, odt, kw):
     (16, 4096, 24, None, {"per_row_a": True}),
     (3, 80, 17, None, {}),
 ])
-def test_gemv_both_kernels(monkeypatch, impl, M, K, N, odt, kw):
+def test_gemv_both_kernels(tune, impl, M, K, N, odt, kw):
     """FP8B_GEMV_IMPL=1: CUDA-core FHFMA kernel; =2: warp-level tensor-core kernel.  Both must meet
     the same tolerance on every M in 1..16."""
-    monkeypatch.setenv("FP8B_GEMV_IMPL", str(impl))
+    tune("GEMV_IMPL", impl)
     _run_case(M, K, N, odt, ALGO_GEMV, seed=impl + M + K + N, **kw)
 
 
@@ -123,15 +123,15 @@ def test_gemv_both_kernels(monkeypatch, impl, M, K, N, odt, kw):
     (30000, 1000, None, {"scale_result": True}),  # K % 512 != 0, 4 vectors per lane
     (16, 2000, None, {}),
 ])
-def test_gemv_rows_kernel(monkeypatch, K, N, odt, kw):
+def test_gemv_rows_kernel(tune, K, N, odt, kw):
     """FP8B_GEMV_IMPL=3: the SM-balanced persistent M=1 kernel (falls back to the warp-per-row kernel
     where it does not apply, e.g. N < 2 x SM count)."""
-    monkeypatch.setenv("FP8B_GEMV_IMPL", "3")
+    tune("GEMV_IMPL", 3)
     _run_case(1, K, N, odt, ALGO_GEMV, seed=K + N, **kw)
 
 
-def test_gemv_rows_nan_bytes(monkeypatch):
-    monkeypatch.setenv("FP8B_GEMV_IMPL", "3")
+def test_gemv_rows_nan_bytes(tune):
+    tune("GEMV_IMPL", 3)
     rng = np.random.default_rng(3)
     A = rng.integers(0, 256, (1, 2048), dtype=np.uint8)
     B = rng.integers(0, 256, (600, 2048), dtype=np.uint8)
@@ -143,8 +143,8 @@ def test_gemv_rows_nan_bytes(monkeypatch):
     _check(C, o.scaled_mm(A, B, sa, sb), None, what="rows nan bytes")
 
 
-def test_gemv_mma_nan_bytes(monkeypatch):
-    monkeypatch.setenv("FP8B_GEMV_IMPL", "2")
+def test_gemv_mma_nan_bytes(tune):
+    tune("GEMV_IMPL", 2)
     rng = np.random.default_rng(1)
     A = rng.integers(0, 256, (5, 1024), dtype=np.uint8)
     B = rng.integers(0, 256, (70, 1024), dtype=np.uint8)
@@ -227,10 +227,10 @@ def test_tcgen05_gemm(M, K, N, odt, kw):
     (2304, 256, 2560, torch.bfloat16, {"per_row_b": True, "bias_dtype": torch.bfloat16}),   # 9x10 pair tiles: 74 + 16 -> last wave split in half-width tiles
     (2304, 128, 2500, None, {"per_row_a": True}),                                         # same, ragged N, fp32 out
 ])
-def test_tcgen05_all_tile_configs(monkeypatch, cfg, M, K, N, odt, kw):
+def test_tcgen05_all_tile_configs(tune, cfg, M, K, N, odt, kw):
     """FP8B_GEMM_CFG: 1 = 128x256 tile, one CTA; 2 = 128x128, one CTA; 3 = 256x256, CTA pair
     (cta_group::2); 4 = 256x128, CTA pair; 5 = 256x192, CTA pair.  Every configuration must serve every shape."""
-    monkeypatch.setenv("FP8B_GEMM_CFG", str(cfg))
+    tune("GEMM_CFG", cfg)
     tol = 1e-4 if odt is None else None
     _run_case(M, K, N, odt, ALGO_TCGEN05, seed=cfg + M + N, tol=tol, **kw)
 

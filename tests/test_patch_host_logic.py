@@ -83,6 +83,12 @@ def test_to_argument_forms_parse():
     assert parse((), {"dtype": torch.bfloat16, "device": torch.device("cpu")}) == (torch.bfloat16, torch.device("cpu"))
     o = torch.zeros(1, dtype=torch.float64)
     assert parse((o,), {}) == (torch.float64, o.device)
+    assert parse((1, torch.float8_e4m3fn), {}) == (torch.float8_e4m3fn, 1)          # to(ordinal, dtype)
+    assert parse((torch.float16, True), {}) == (torch.float16, None)                # to(dtype, non_blocking)
+    assert parse((True,), {}) == (None, None)
+    assert fp8_mps_patch._device_type(2) == "cuda" and fp8_mps_patch._device_type(True) is None
+    assert fp8_mps_patch._as_device(3) == torch.device("cuda", 3)
+    assert fp8_mps_patch._as_device("cuda:1") == torch.device("cuda", 1)
     assert fp8_mps_patch._device_type("cuda:3") == "cuda"
     assert fp8_mps_patch._device_type(torch.device("cpu")) == "cpu"
     assert fp8_mps_patch._is_fp8_dtype(torch.float8_e4m3fn) and fp8_mps_patch._is_fp8_dtype(torch.float8_e5m2)
@@ -116,3 +122,45 @@ def test_scaled_mm_wrapper_accepts_positional_and_keyword_scales():
 
 def test_vae_stub_is_callable():
     fp8_mps_patch.patch_vae_decode_for_mps_limits()
+
+
+def test_repo_root_loads_as_a_comfyui_custom_node(tmp_path, capsys):
+    """ComfyUI imports custom_nodes/<clone>/__init__.py by path (reference: __init__.py:22-61).  The repo root must
+    install the patches and export the (empty) node mappings, exactly like the reference's root module."""
+    import importlib.util
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fp8_mps_patch.uninstall()
+    fake = types.ModuleType("comfy")
+    had = sys.modules.get("comfy")
+    sys.modules["comfy"] = fake
+    try:
+        spec = importlib.util.spec_from_file_location("fp8_b200_custom_node", os.path.join(root, "__init__.py"),
+                                                      submodule_search_locations=[root])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.NODE_CLASS_MAPPINGS == {} and mod.NODE_DISPLAY_NAME_MAPPINGS == {}
+        assert mod.__all__ == ["NODE_CLASS_MAPPINGS", "NODE_DISPLAY_NAME_MAPPINGS"]
+        assert fp8_mps_patch.is_installed()
+        assert torch._scaled_mm is fp8_mps_patch._metal_scaled_mm
+        out = capsys.readouterr().out
+        assert "installed" in out.lower()
+        spec.loader.exec_module(mod)                           # second load: idempotent (reference __init__.py:39-40)
+        assert "already installed" in capsys.readouterr().out
+    finally:
+        fp8_mps_patch.uninstall()
+        if had is None:
+            sys.modules.pop("comfy", None)
+        else:
+            sys.modules["comfy"] = had
+
+
+def test_pyproject_has_comfy_registry_fields():
+    import tomllib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "pyproject.toml"), "rb") as f:
+        meta = tomllib.load(f)
+    comfy = meta["tool"]["comfy"]                                # reference pyproject.toml:12-15
+    assert comfy["PublisherId"] and comfy["DisplayName"]
+    assert meta["project"]["name"] and meta["project"]["version"]
