@@ -2,29 +2,35 @@
 """
 bench.py -- measures the FP8 hot path on B200 and prints ONE JSON line (rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sub]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-sub] [--no-cpu]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Headline (BASELINE.json configs[1], "C2"): `_scaled_mm` GEMV M=1 K=14336 N=4096, bf16 out, HBM-bound.
-  * a STEP is one batch of 128 GEMV calls: 8 passes over a rotation of 16 distinct weight matrices
-    (16 x 58.7 MB = 940 MB, far larger than the 126 MB L2, so every call streams its weights from
-    HBM); the step is captured once in a CUDA graph and replayed, timed with CUDA events on the
-    launching stream after W warm-up replays, barrier + synchronize on both sides, MAX over ranks.
-  * value  = algorithmic bytes of all ranks / time  (58 742 784 B per call), inputs
-             resident in HBM.
-  * e2e    = the same metric through the reference-facing call `torch._scaled_mm(...)` after
-             fp8_mps_patch.install(), with HOST (pinned) buffers: every step copies x and W host->device,
-             runs the op and reads the result back device->host.
-  * roofline = that kernel's algorithmic bytes / its average launch duration over the timed region,
-             against MEASURED_PEAKS.json's copy bandwidth.
-  * cpu_baseline = the oracle port of the reference's CPU path (LUT dequantise + fp32 matmul) on
-             the host cores, bounded sample.
-N > 1: the GEMV does not shard usefully -> independent replicas, weak scaling; the
-N-sharded FLUX linear (C4) + NCCL all-gather is measured in `sub`.
-`sub` carries the other BASELINE configs (C1, C3, C4, C5) with their own rooflines.
+Headline at every N (BASELINE.json `metric` names "_scaled_mm TFLOPS" first; configs[3], "C4", is the config that
+shards): the FLUX.1-dev-shaped DiT linear  `_scaled_mm`  M=4096 K=3072 N=12288, FP8 e4m3fn operands, per-tensor
+scales, bf16 out -- 309 237 645 312 flops per call.
+  * a STEP is 4 calls over a rotation of 4 distinct (A, W, C) sets (4 x 151 MB, larger than the 126 MB L2).
+  * N = 1: the tcgen05 kernel through the C ABI, the step captured in a CUDA graph.
+    N > 1: STRONG scaling of the same problem: W is column-sharded over the ranks (ShardedScaledMM, mode "push"):
+    ONE kernel per rank computes its (M, N/w) block on the tensor cores and pushes every finished box with TMA stores
+    into the row-major (M, N) result of EVERY rank over NVLink; one symmetric-memory barrier closes the call.  A call
+    is complete when every rank holds the full result.
+  * value   = flops of all calls / time, CUDA events on the launching stream after W (>= 3) warm-up steps, barrier +
+              synchronize on both sides, MAX over ranks.  Inputs resident in HBM.
+  * e2e     = the same call through the public API with HOST (pinned) buffers inside the timed region:
+              N = 1: fp8_mps_patch.install(); torch._scaled_mm(...) with A and W copied host->device and C copied
+              device->host every step;  N > 1: ShardedScaledMM with A and this rank's W shard copied in and this
+              rank's 1/N row slab of the assembled result copied out (the ranks' slabs make up exactly one C).
+  * roofline = the GEMM kernel's flops / its average duration in the timed region against 2 x the measured bf16
+              cuBLAS rate of MEASURED_PEAKS.json (dense-FP8 proxy); at N > 1 also the NVLink floor of the exchange.
+  * sharded (N > 1): every exchange plan timed, each with `parity` = bit-equal to the un-sharded GEMM on every rank
+              and <= 3e-3 rel-RMSE against the CPU oracle on a 64-row slab.
+  * cpu_baseline = the oracle port of the reference's CPU path (LUT dequantise + fp32 matmul) on the host cores.
+`sub` (N = 1) carries the other BASELINE configs with their own rooflines: C2 (M=1 K=14336 N=4096 GEMV, HBM-bound),
+C1, C3, the reference's own square benchmark shape (M=1 K=N=14336, test_fp8_metal.py:232-236), C5 (FLUX-sized cast
+sweeps) and the un-patched torch._scaled_mm (cuBLASLt FP8) time on C4 as a library yardstick.
 
---impl reference: the reference's CPU implementation of the same workload (oracle port, all host
-threads), same JSON shape with "impl": "reference".
+--impl reference: the reference's CPU implementation of the same workload (oracle port, all host threads), same
+`config`, same JSON shape with "impl": "reference".
 """
 
 from __future__ import annotations
@@ -55,11 +61,29 @@ C3 = dict(M=4, K=4096, N=4096)
 C3_BYTES = 16_834_560
 C4 = dict(M=4096, K=3072, N=12288)
 C4_FLOPS = 309_237_645_312
+C4_OUT_BYTES = 100_663_296
+SQ = dict(M=1, K=14336, N=14336)           # the reference's own benchmark shape (test_fp8_metal.py:232-236; README.md:80: 2.38 ms)
+SQ_BYTES = 14336 * 14336 + 14336 + 2 * 14336 + 8
 ROTATION = 16
 PASSES = 8
+SETS = 4                                   # C4 rotation: 4 x (12.6 + 37.7 + 100.7) MB > 126 MB L2
+NVLINK_GBS = 770.0                         # measured peer-copy rate per direction per GPU (B200_PROFILING.md)
 
 FALLBACK_HBM_GBS = 6650.0                  # B200_PROFILING.md fallback
 FALLBACK_BF16_TFLOPS = 1590.0
+
+WORKLOAD = ("C4 _scaled_mm FLUX.1-dev DiT linear M=4096 K=3072 N=12288, FP8 e4m3fn, per-tensor scales, bf16 out "
+            "(BASELINE.json configs[3]); N-sharded over the GPUs when N > 1, full row-major result on every rank")
+
+
+def config_for(n_gpus):
+    """The `config` object -- identical in the `ours` and `reference` arms."""
+    return {"workload": WORKLOAD,
+            "step": f"{SETS} _scaled_mm calls over a rotation of {SETS} distinct (A, W, C) sets",
+            "l2": f"inputs larger than L2: rotation of {SETS} sets x 151 MB",
+            "flops_per_call": C4_FLOPS,
+            "parallelism": "single-gpu" if n_gpus == 1 else f"W column-sharded x{n_gpus}, strong scaling",
+            "arith": "e4m3 operands, exact products, fp32 accumulation"}
 
 
 def load_peaks():
@@ -74,10 +98,13 @@ def load_peaks():
 
 def profile_traffic(name):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed ncu capture
-    profiles/r1_<name>_raw.csv (one `ncu --set full` capture of the same kernel and shape), or None."""
+    profiles/r2_<name>_raw.csv (else r1_), one `ncu --set full` capture of the same kernel and shape, or None."""
     import csv
-    path = os.path.join(ROOT, "profiles", f"r1_{name}_raw.csv")
-    if not os.path.exists(path):
+    for rnd in ("r2", "r1"):
+        path = os.path.join(ROOT, "profiles", f"{rnd}_{name}_raw.csv")
+        if os.path.exists(path):
+            break
+    else:
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot = 0.0
@@ -217,60 +244,67 @@ def max_over_ranks(torch, dist, ms):
 
 # --------------------------------------------------------------------------- CPU baseline (oracle port)
 
-def cpu_gemv_baseline(seconds_budget=12.0):
-    """The reference's CPU path for C2 on the host cores: (a) numpy LUT dequantise + fp32 BLAS matmul
-    (what test_fp8_metal.py:257-271 does without the MPS hop), (b) the plain-C restatement of the shader
-    loop on all cores.  Reports the faster; bounded to a few calls."""
+def _cpu_c4_inputs():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
-    import c_oracle
     import fp8_oracle as o
     rng = np.random.default_rng(2)
-    x = o.encode(rng.standard_normal((1, C2["K"])).astype(np.float32) * 50)
-    W = o.encode(rng.standard_normal((C2["N"], C2["K"])).astype(np.float32) * 50)
-    sa = np.array([0.01], np.float32)
-    sb = np.array([0.01], np.float32)
+    A = o.encode(rng.standard_normal((C4["M"], C4["K"])).astype(np.float32) * 50)
+    W = o.encode(rng.standard_normal((C4["N"], C4["K"])).astype(np.float32) * 50)
+    return A, W, np.array([0.01], np.float32), np.array([0.01], np.float32)
+
+
+def _cpu_c4_candidates(A, W, sa, sb):
+    """The reference's CPU path for C4 on the host cores, three statements of it, the fastest is reported:
+    (a) torch CPU FP8 cast + fp32 matmul (the reference's own fallback, test_fp8_metal.py:257-271, minus the MPS hop),
+    (b) numpy LUT dequantise + fp32 BLAS matmul, both full size; (c) the plain-C restatement of the shader loop
+    (fp8_matmul.metal:99-147) on all cores, on a 256-row slab (it is far slower).  Returns {name: (fn, flops, what, cores)}."""
+    import c_oracle
+    import fp8_oracle as o
+    rows = 256
+    import torch
+    return {"torch_cpu": (lambda: o.scaled_mm_torch_cpu(A, W, sa, sb, out_dtype="bf16"), float(C4_FLOPS),
+                          "full-size C4 call (torch CPU FP8 cast of A and W + fp32 matmul + epilogue)", torch.get_num_threads()),
+            "numpy_blas": (lambda: o.scaled_mm(A, W, sa, sb, out_dtype="bf16", accum="f32"), float(C4_FLOPS),
+                           "full-size C4 call (LUT dequantise of A and W + sgemm + epilogue)", os.cpu_count() or 1),
+            "c_threads": (lambda: c_oracle.scaled_mm(A[:rows], W, sa, sb), float(C4_FLOPS) * rows / C4["M"],
+                          f"{rows}-row slab of C4 (1/{C4['M'] // rows} of the call), shader-loop port on pthreads",
+                          c_oracle.num_threads())}
+
+
+def cpu_c4_baseline(seconds_budget=20.0):
+    A, W, sa, sb = _cpu_c4_inputs()
     res = {}
-    for name, fn in (("c_threads", lambda: c_oracle.scaled_mm(x, W, sa, sb)),
-                     ("numpy_blas", lambda: o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"))):
-        fn()
-        best = float("inf")
+    for name, (fn, flops, what, cores) in _cpu_c4_candidates(A, W, sa, sb).items():
+        t0 = time.perf_counter(); fn(); first = time.perf_counter() - t0          # warm-up (page faults, thread pool)
+        best, n = first, 0
         t_start = time.perf_counter()
-        n = 0
-        while n < 5 and time.perf_counter() - t_start < seconds_budget / 2:
-            t0 = time.perf_counter()
-            fn()
-            best = min(best, time.perf_counter() - t0)
-            n += 1
-        res[name] = (best, n)
-    pick = min(res, key=lambda k: res[k][0])
-    cores = c_oracle.num_threads() if pick == "c_threads" else (os.cpu_count() or 1)
-    return {"value": round(C2_BYTES / res[pick][0] / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": f"{res[pick][1]} full-size C2 GEMV calls (M=1 K=14336 N=4096), best; {pick}",
-            "ms_per_call": round(res[pick][0] * 1e3, 3),
-            "alt": {k: round(v[0] * 1e3, 3) for k, v in res.items()}}
+        while n < 3 and time.perf_counter() - t_start < seconds_budget / 2:
+            t0 = time.perf_counter(); fn(); best = min(best, time.perf_counter() - t0); n += 1
+        res[name] = (flops / best / 1e12, best, n, what, cores)
+    pick = max(res, key=lambda k: res[k][0])
+    tf, best, n, what, cores = res[pick]
+    return {"value": round(tf, 4), "unit": "TFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"{max(n, 1)} x {what}, best; {pick}", "s_per_sample": round(best, 4),
+            "alt_tflops": {k: round(v[0], 4) for k, v in res.items()}}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import c_oracle
-    import fp8_oracle as o
-    rng = np.random.default_rng(2)
-    x = o.encode(rng.standard_normal((1, C2["K"])).astype(np.float32) * 50)
-    W = o.encode(rng.standard_normal((C2["N"], C2["K"])).astype(np.float32) * 50)
-    sa = np.array([0.01], np.float32)
-    sb = np.array([0.01], np.float32)
-    t_c = time.perf_counter(); c_oracle.scaled_mm(x, W, sa, sb); t_c = time.perf_counter() - t_c
-    t_n = time.perf_counter(); o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"); t_n = time.perf_counter() - t_n
-    use_c = t_c <= t_n
-    fn = (lambda: c_oracle.scaled_mm(x, W, sa, sb)) if use_c else \
-        (lambda: o.scaled_mm(x, W, sa, sb, out_dtype="bf16", accum="f32"))
-    calls_per_step = 2                          # bounded sample of the 128-call step
-    for _ in range(max(args.warmup, 3)):         # W >= 3 warm-up steps, like the GPU arm
+    A, W, sa, sb = _cpu_c4_inputs()
+    cands = _cpu_c4_candidates(A, W, sa, sb)
+    probe = {}
+    for name, (fn, flops, what, cores) in cands.items():
+        fn()
+        t0 = time.perf_counter(); fn(); probe[name] = flops / (time.perf_counter() - t0)
+    pick = max(probe, key=probe.get)
+    fn, flops, what, cores = cands[pick]
+    t_call = flops / probe[pick]
+    # bounded sample: one call per step; the whole run stays within a few minutes
+    calls_per_step = SETS if t_call * SETS * (args.steps + max(args.warmup, 3)) < 150.0 else 1
+    for _ in range(max(args.warmup, 3)):
         for _ in range(calls_per_step):
             fn()
     t0 = time.perf_counter()
@@ -278,17 +312,16 @@ def run_reference(args):
         for _ in range(calls_per_step):
             fn()
     dt = time.perf_counter() - t0
-    value = C2_BYTES * calls_per_step * args.steps / dt / 1e9
-    cores = c_oracle.num_threads() if use_c else (os.cpu_count() or 1)
+    value = flops * calls_per_step * args.steps / dt / 1e12
     line = {
-        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 _scaled_mm GEMV M=1 K=14336 N=4096 bf16-out, CPU oracle port of the reference path",
-                   "calls_per_step": calls_per_step, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": "port",
-                         "sample": f"{calls_per_step} full-size C2 calls per step ({'C threads' if use_c else 'numpy LUT + BLAS'})"},
-        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_for(args.gpus),
+        "cpu_baseline": {"value": round(value, 4), "unit": "TFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"{calls_per_step} x {what} per step; {pick}",
+                         "calls_per_step": calls_per_step, "gpu_arm_calls_per_step": SETS},
+        "e2e": {"value": round(value, 4), "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
@@ -491,6 +524,166 @@ def bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup):
     return out
 
 
+# --------------------------------------------------------------------------- C2 GEMV block (a `sub` entry since round 2)
+
+def bench_c2(torch, L, gen, dev, peaks, steps, warmup):
+    """BASELINE configs[1]: M=1 K=14336 N=4096 bf16 out.  128 calls per step = 8 passes over 16 distinct weight
+    matrices (940 MB >> L2) in one CUDA graph; plus the static-weights PDL option, four forked streams, the
+    four-per-launch batched entry point, and the patched torch._scaled_mm with resident weights (host x in, y out)."""
+    from _util import GemvItem, dt_code
+    import fp8_mps_patch
+    M, K, N = C2["M"], C2["K"], C2["N"]
+    x, inv_x = _rand_fp8(torch, (M, K), gen, dev)
+    Ws, inv_ws = [], []
+    for _ in range(ROTATION):
+        w, inv_w = _rand_fp8(torch, (N, K), gen, dev)
+        Ws.append(w)
+        inv_ws.append(inv_w)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    bf16 = dt_code(torch.bfloat16)
+    calls = ROTATION * PASSES
+
+    def step():
+        for _ in range(PASSES):
+            for w, s in zip(Ws, inv_ws):
+                _mm(L, torch, x, w, out, bf16, inv_x, s)
+
+    def gbs(ms):
+        return C2_BYTES * calls / (ms / steps * 1e-3) / 1e9
+
+    ms, launches, _, _ = time_graph(torch, step, steps, warmup)
+    L.fp8b_set_option(1, 1)
+    try:
+        ms_static, _, _, _ = time_graph(torch, step, steps, warmup)
+    finally:
+        L.fp8b_set_option(1, 0)
+    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
+    outs4 = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+
+    def step_streams():
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for s_ in side:
+            s_.wait_event(fork)
+        i = 0
+        for _ in range(PASSES):
+            for w, sc in zip(Ws, inv_ws):
+                with torch.cuda.stream(side[i % 4]):
+                    _mm(L, torch, x, w, outs4[i % 4], bf16, inv_x, sc)
+                i += 1
+        for s_ in side:
+            j = torch.cuda.Event()
+            j.record(s_)
+            cur.wait_event(j)
+
+    ms_streams, _, _, _ = time_graph(torch, step_streams, steps, warmup)
+    groups = []
+    for g0 in range(0, ROTATION, 4):
+        arr = (GemvItem * 4)()
+        for j in range(4):
+            w, sc = Ws[g0 + j], inv_ws[g0 + j]
+            arr[j].x, arr[j].W, arr[j].y, arr[j].N = x.data_ptr(), w.data_ptr(), outs4[j].data_ptr(), N
+            arr[j].scale_x, arr[j].scale_w, arr[j].scale_w_len, arr[j].bias = inv_x.data_ptr(), sc.data_ptr(), 1, None
+        groups.append(arr)
+
+    def step_batched():
+        sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for _ in range(PASSES):
+            for arr in groups:
+                rc = L.fp8b_gemv_batch(arr, 4, K, bf16, 0, sp)
+                assert rc == 0, rc
+
+    ms_b, launches_b, _, _ = time_graph(torch, step_batched, steps, warmup)
+    us = ms / steps * 1e3 / calls
+    res = {"us_per_call": round(us, 3), "value": round(gbs(ms), 1), "unit": "GB/s",
+           "roofline": {"bound": "hbm", "achieved": round(gbs(ms), 1), "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": round(gbs(ms) / peaks["hbm"], 4), "frac_of_nominal_8000": round(gbs(ms) / 8000.0, 4),
+                        "traffic": profile_traffic("gemv"), "peak_source": peaks["source"], "algorithmic_bytes": C2_BYTES},
+           "step": f"{calls} GEMV calls = {PASSES} passes over {ROTATION} distinct weight matrices (940 MB), one CUDA graph",
+           "launches_per_step": int(launches),
+           "static_weights_pdl": {"us_per_call": round(ms_static / steps * 1e3 / calls, 3), "value": round(gbs(ms_static), 1),
+                                  "note": "opt-in FP8B_OPT_STATIC_WEIGHTS=1"},
+           "four_streams": {"us_per_call": round(ms_streams / steps * 1e3 / calls, 3), "value": round(gbs(ms_streams), 1),
+                            "frac": round(gbs(ms_streams) / peaks["hbm"], 4),
+                            "note": "the same 128 independent calls round-robin on 4 forked streams"},
+           "batched_gemv": {"us_per_gemv": round(ms_b / steps * 1e3 / calls, 3), "value": round(gbs(ms_b), 1),
+                            "frac": round(gbs(ms_b) / peaks["hbm"], 4), "launches_per_step": int(launches_b),
+                            "note": "fp8b_gemv_batch: four independent C2 GEMVs per launch"}}
+    # the deployment shape of the plug-in: weights resident, x from / y to pinned host memory, patched torch._scaled_mm
+    with contextlib.redirect_stdout(sys.stderr):
+        fp8_mps_patch.install()
+    try:
+        hx = x.cpu().pin_memory()
+        hout = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
+        dx = torch.empty_like(x)
+        w8s = [w.view(torch.float8_e4m3fn).t() for w in Ws]
+
+        def e2e_resident(i):
+            dx.copy_(hx, non_blocking=True)
+            y = torch._scaled_mm(dx.view(torch.float8_e4m3fn), w8s[i % ROTATION], inv_x, inv_ws[i % ROTATION], None, None,
+                                 torch.bfloat16)
+            hout.copy_(y, non_blocking=True)
+
+        for i in range(16):
+            e2e_resident(i)
+        torch.cuda.synchronize()
+        r0 = torch.cuda.Event(enable_timing=True)
+        r1 = torch.cuda.Event(enable_timing=True)
+        n_it = 256
+        t_h0 = time.perf_counter()
+        r0.record()
+        for i in range(n_it):
+            e2e_resident(i)
+        r1.record()
+        t_h1 = time.perf_counter()
+        torch.cuda.synchronize()
+        res_ms = r0.elapsed_time(r1) / n_it
+        res["e2e_resident_weights"] = {
+            "value": round(C2_BYTES / (res_ms * 1e-3) / 1e9, 1), "unit": "GB/s", "us_per_step": round(res_ms * 1e3, 2),
+            "host_us_per_step": round((t_h1 - t_h0) / n_it * 1e6, 2),
+            "frac_of_device_value": round(C2_BYTES / (res_ms * 1e-3) / 1e9 / gbs(ms), 3),
+            "h2d_bytes_per_step": int(hx.numel()), "d2h_bytes_per_step": int(hout.numel() * 2),
+            "note": "patched torch._scaled_mm; weights on the GPU (16-matrix rotation, HBM-cold); x copied in and y copied "
+                    "out of pinned host memory every step"}
+    finally:
+        fp8_mps_patch.uninstall()
+    return res
+
+
+def bench_library_yardstick(torch, bufs, steps, warmup):
+    """Un-patched torch._scaled_mm (cuBLASLt FP8) on the same C4 rotation: the library sanity bar SURVEY 2.2 allows."""
+    one = torch.ones((), device=bufs[0][0].device)
+
+    def step():
+        for a, inv_a, w, inv_w, out in bufs:
+            torch._scaled_mm(a.view(torch.float8_e4m3fn), w.view(torch.float8_e4m3fn).t(), inv_a.reshape(()), inv_w.reshape(()),
+                             None, None, torch.bfloat16, False)
+    try:
+        step()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        for _ in range(max(warmup, 3)):
+            g.replay()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (steps * len(bufs))
+        del one
+        return {"us_per_call": round(us, 2), "tflops": round(C4_FLOPS / (us * 1e-6) / 1e12, 1),
+                "what": "stock torch._scaled_mm (cuBLASLt FP8, fast_accum off), same rotation and CUDA graph; a yardstick, "
+                        "not part of the product path"}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)[:300]}
+
+
 # --------------------------------------------------------------------------- main
 
 _JSON_OUT = None
@@ -500,6 +693,33 @@ def emit(line):
     out = _JSON_OUT or sys.stdout
     out.write(json.dumps(line) + "\n")
     out.flush()
+
+
+def pin_to_gpu_numa_node(torch, index):
+    """Best effort: run this rank's host thread (and so first-touch its pinned buffers) on the CPUs of the NUMA node
+    the GPU hangs off, so that N ranks' host<->device copies do not all cross one memory controller."""
+    try:
+        prop_id = torch.cuda.get_device_properties(index).pci_bus_id
+        bus = f"0000:{prop_id:02x}:00.0" if isinstance(prop_id, int) else str(prop_id).lower()
+        if not os.path.exists(f"/sys/bus/pci/devices/{bus}"):
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"node {node}, {len(allowed)} cpus"
+        return f"node {node} outside this process's cpuset"
+    except Exception as e:
+        return f"not pinned: {type(e).__name__}"
 
 
 def main():
@@ -536,276 +756,282 @@ def main():
     else:
         torch.cuda.set_device(0)
     dev = torch.device("cuda", torch.cuda.current_device())
+    numa = pin_to_gpu_numa_node(torch, torch.cuda.current_device())
     n_gpus = world
+    steps = max(args.steps, 1)
+    warmup = max(args.warmup, 3)
     peaks = load_peaks()
+    fp8_peak = 2 * peaks["bf16"]
     L = _capi()                                    # fails loudly if libfp8_b200.so is missing
     import fp8_mps_native
     import fp8_mps_patch
-    gen = torch.Generator(device=dev).manual_seed(1 + rank)
-
-    # ---------------- headline: C2 GEMV, HBM-resident, graph of ROTATION x PASSES calls
-    M, K, N = C2["M"], C2["K"], C2["N"]
-    x, inv_x = _rand_fp8(torch, (M, K), gen, dev)
-    Ws, inv_ws = [], []
-    for _ in range(ROTATION):
-        w, inv_w = _rand_fp8(torch, (N, K), gen, dev)
-        Ws.append(w)
-        inv_ws.append(inv_w)
-    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    M, K, N = C4["M"], C4["K"], C4["N"]
     bf16 = dt_code(torch.bfloat16)
 
-    def step():
-        for _ in range(PASSES):
-            for w, s in zip(Ws, inv_ws):
-                _mm(L, torch, x, w, out, bf16, inv_x, s)
+    # ---------------- data: the SAME four (A, W) sets on every rank (same seeds), randn -> reference-codec FP8 on the device
+    bufs = []
+    for i in range(SETS):
+        g = torch.Generator(device=dev).manual_seed(100 + i)
+        a, inv_a = _rand_fp8(torch, (M, K), g, dev)
+        w, inv_w = _rand_fp8(torch, (N, K), g, dev)
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        bufs.append((a, inv_a, w, inv_w, out))
 
+    def step_single():
+        for a, inv_a, w, inv_w, out in bufs:
+            _mm(L, torch, a, w, out, bf16, inv_a, inv_w, algo=2)
+
+    sharded = None
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
-    ms, launches_per_step, t0, t1 = time_graph(torch, step, args.steps, args.warmup, dist)
-    clocks = sampler.summary(t0, t1)
-    ms = max_over_ranks(torch, dist, ms)
-    L.fp8b_set_option(1, 1)                        # opt-in variant, reported beside the headline (not as it)
-    try:
-        ms_static, _, _, _ = time_graph(torch, step, args.steps, args.warmup, dist)
-    finally:
-        L.fp8b_set_option(1, 0)
-    ms_static = max_over_ranks(torch, dist, ms_static)
+    if n_gpus == 1:
+        ms, launches_per_step, t0, t1 = time_graph(torch, step_single, steps, warmup)
+        clocks = sampler.summary(t0, t1)
+        kernel_us = ms / steps * 1e3 / SETS
+        kernel_name = "fp8b::fp8_gemm_tcgen05_kernel<256,2,0> (CTA pairs, 256x256 tiles)"
+    else:
+        from fp8_sharded import ShardedScaledMM, shard_bounds
+        lins = [ShardedScaledMM(w, inv_w, None) for (_, _, w, inv_w, _) in bufs]       # each keeps its own shard of W
+        n0, n1, width = shard_bounds(N, n_gpus, rank)
 
-    # variant: the same 128 independent calls issued round-robin on 4 forked streams (each with its own output)
-    side = [torch.cuda.Stream(device=dev) for _ in range(4)]
-    outs4 = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+        def plan_step(mode, layout="row_major"):
+            def run():
+                for lin, (a, inv_a, _, _, _) in zip(lins, bufs):
+                    lin(a, inv_a, torch.bfloat16, layout=layout, mode=mode)
+            return run
 
-    def step_streams():
-        cur = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(cur)
-        for s_ in side:
-            s_.wait_event(fork)
-        i = 0
-        for _ in range(PASSES):
-            for w, sc in zip(Ws, inv_ws):
-                with torch.cuda.stream(side[i % 4]):
-                    _mm(L, torch, x, w, outs4[i % 4], bf16, inv_x, sc)
-                i += 1
-        for s_ in side:
-            j = torch.cuda.Event()
-            j.record(s_)
-            cur.wait_event(j)
+        # parity of every plan BEFORE anything is timed: bit-equal to the un-sharded GEMM on every rank, and a 64-row
+        # slab of the un-sharded result against the CPU oracle
+        step_single()
+        torch.cuda.synchronize()
+        a0, inv_a0, w0, inv_w0, full0 = bufs[0]
+        oracle_err = None
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import fp8_oracle as o
+            ref = o.scaled_mm(a0[:64].cpu().numpy(), w0.cpu().numpy(), inv_a0.cpu().numpy(), inv_w0.cpu().numpy(), None, None,
+                              "bf16", accum="f32")
+            oracle_err = float(o.rel_rmse(full0[:64].float().cpu().numpy(), ref))
+        plans = {"push_fused": ("push", "row_major"), "peer_store_fused": ("peers", "row_major"),
+                 "multicast_fused": ("multicast", "row_major"), "allgather_row_major": ("allgather", "row_major"),
+                 "allgather_rank_major": ("allgather", "rank_major")}
+        sharded = {"world": n_gpus, "exchange_recv_bytes_per_gpu": int((n_gpus - 1) * M * (n1 - n0) * 2),
+                   "oracle_slab_rel_rmse_unsharded": oracle_err, "plans": {}}
+        for name, (mode, layout) in plans.items():
+            entry = {}
+            try:
+                y = lins[0](a0, inv_a0, torch.bfloat16, layout=layout, mode=mode)
+                if layout == "rank_major":
+                    y = y.permute(1, 0, 2).reshape(M, -1)[:, :N]
+                torch.cuda.synchronize()
+                same = torch.tensor([1 if torch.equal(y, full0) else 0], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                entry["parity"] = bool(int(same.item()) == 1) and (oracle_err is None or oracle_err <= 3e-3)
+                entry["bit_equal_to_unsharded_on_every_rank"] = bool(int(same.item()) == 1)
+                fn = plan_step(mode, layout)
+                for _ in range(warmup):
+                    fn()
+                torch.cuda.synchronize()
+                dist.barrier()
+                torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                n0_l = L.fp8b_launch_count()
+                tw0 = time.perf_counter()
+                e0.record()
+                for _ in range(steps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tw1 = time.perf_counter()
+                dist.barrier()
+                t_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1))
+                entry["us_per_call"] = round(t_ms / steps * 1e3 / SETS, 2)
+                entry["tflops_total"] = round(C4_FLOPS / (entry["us_per_call"] * 1e-6) / 1e12, 1)
+                entry["launches_per_step"] = int((L.fp8b_launch_count() - n0_l) // steps)
+                entry["_ms"], entry["_t0"], entry["_t1"] = t_ms, tw0, tw1
+            except Exception as e:
+                entry["error"] = repr(e)[:200]
+                entry["parity"] = False
+            sharded["plans"][name] = entry
+        # compute only (no exchange): this rank's shard through the plain kernel
+        def step_local():
+            for lin, (a, inv_a, _, _, _) in zip(lins, bufs):
+                lin.local(a, inv_a, torch.bfloat16)
+        ms_l, _, _, _ = time_graph(torch, step_local, steps, warmup, dist)
+        sharded["shard_gemm_only_us"] = round(max_over_ranks(torch, dist, ms_l) / steps * 1e3 / SETS, 2)
+        head = sharded["plans"]["push_fused"]
+        if "us_per_call" not in head:
+            raise RuntimeError(f"push plan failed: {head}")
+        ms, t0, t1 = head.pop("_ms"), head.pop("_t0"), head.pop("_t1")
+        for e in sharded["plans"].values():
+            for k in ("_ms", "_t0", "_t1"):
+                e.pop(k, None)
+        launches_per_step = head["launches_per_step"]
+        clocks = sampler.summary(t0, t1)
+        kernel_us = head["us_per_call"]
+        kernel_name = "fp8b::fp8_gemm_tcgen05_kernel<BN,2,2> (tcgen05 GEMM + TMA push to every rank), incl. the closing barrier"
+        floor_link = (n_gpus - 1) / n_gpus * C4_OUT_BYTES / (NVLINK_GBS * 1e9) * 1e6
+        floor_mma = C4_FLOPS / n_gpus / (fp8_peak * 1e12) * 1e6
+        sharded["floor_us"] = {"nvlink_770GBs": round(floor_link, 1), "tensor_at_measured_peak": round(floor_mma, 1),
+                               "bound": round(max(floor_link, floor_mma), 1),
+                               "achieved_over_bound": round(max(floor_link, floor_mma) / kernel_us, 3)}
+        sharded["best_plan"] = min((k for k, v in sharded["plans"].items() if "us_per_call" in v and v.get("parity")),
+                                   key=lambda k: sharded["plans"][k]["us_per_call"], default=None)
+        sharded["parity"] = {k: bool(v.get("parity")) for k, v in sharded["plans"].items()}
 
-    ms_streams, _, _, _ = time_graph(torch, step_streams, args.steps, args.warmup, dist)
-    ms_streams = max_over_ranks(torch, dist, ms_streams)
-    # the same 128 GEMVs issued four per launch through fp8b_gemv_batch (independent projections sharing a launch)
-    batched = None
-    try:
-        from _util import GemvItem
-        groups = []
-        outs_b = [torch.empty(M, N, dtype=torch.bfloat16, device=dev) for _ in range(4)]
-        for g0 in range(0, ROTATION, 4):
-            arr = (GemvItem * 4)()
-            for j in range(4):
-                w, sc = Ws[g0 + j], inv_ws[g0 + j]
-                arr[j].x, arr[j].W, arr[j].y, arr[j].N = x.data_ptr(), w.data_ptr(), outs_b[j].data_ptr(), N
-                arr[j].scale_x, arr[j].scale_w, arr[j].scale_w_len, arr[j].bias = inv_x.data_ptr(), sc.data_ptr(), 1, None
-            groups.append(arr)
-
-        def step_batched():
-            sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            for _ in range(PASSES):
-                for arr in groups:
-                    rc = L.fp8b_gemv_batch(arr, 4, K, bf16, 0, sp)
-                    assert rc == 0, rc
-
-        ms_b, launches_b, _, _ = time_graph(torch, step_batched, args.steps, args.warmup, dist)
-        ms_b = max_over_ranks(torch, dist, ms_b)
-        batched = {"value": round(n_gpus * C2_BYTES * ROTATION * PASSES / (ms_b / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
-                   "us_per_gemv": round(ms_b / args.steps * 1e3 / (ROTATION * PASSES), 3), "launches_per_step": int(launches_b),
-                   "frac": round(C2_BYTES * ROTATION * PASSES / (ms_b / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
-                   "note": "fp8b_gemv_batch: four independent C2 GEMVs (one x, four weight matrices) per launch, same graph and "
-                           "rotation; the launch ramp-up and drain are paid once per four"}
-    except Exception as e:  # pragma: no cover
-        batched = {"error": repr(e)[:200]}
-
-    calls = ROTATION * PASSES
-    ms_per_step = ms / args.steps
-    us_per_call = ms_per_step * 1e3 / calls
-    value = n_gpus * C2_BYTES * calls / (ms_per_step * 1e-3) / 1e9
+    ms = max_over_ranks(torch, dist, ms) if n_gpus == 1 else ms
+    ms_per_step = ms / steps
+    us_per_call = ms_per_step * 1e3 / SETS
+    value = C4_FLOPS / (us_per_call * 1e-6) / 1e12             # whole job: one problem, N GPUs
     per_gpu = value / n_gpus
 
-    # ---------------- e2e: patched torch._scaled_mm with pinned HOST buffers, copies inside the timed region
-    with contextlib.redirect_stdout(sys.stderr):      # install() prints like the reference; stdout carries the JSON line only
+    # ---------------- e2e: the public call with pinned HOST buffers, copies inside the timed region
+    a, inv_a, w, inv_w, _ = bufs[0]
+    e2e_steps = max(min(steps, 10), 3)
+    with contextlib.redirect_stdout(sys.stderr):
         fp8_mps_patch.install()
     try:
-        hx = x.cpu().pin_memory()
-        hW = Ws[0].cpu().pin_memory()
-        hout = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
-        dx = torch.empty_like(x)
-        dW = torch.empty_like(Ws[0])
-        sa_d, sb_d = inv_x, inv_ws[0]
+        hA = a.cpu().pin_memory()
+        dA = torch.empty_like(a)
+        if n_gpus == 1:
+            hW = w.cpu().pin_memory()
+            dW = torch.empty_like(w)
+            hC = torch.empty(M, N, dtype=torch.bfloat16).pin_memory()
 
-        def e2e_step():
-            dx.copy_(hx, non_blocking=True)
-            dW.copy_(hW, non_blocking=True)
-            y = torch._scaled_mm(dx.view(torch.float8_e4m3fn), dW.view(torch.float8_e4m3fn).t(), sa_d, sb_d, None, None,
-                                 torch.bfloat16)
-            hout.copy_(y, non_blocking=True)
+            def e2e_step():
+                dA.copy_(hA, non_blocking=True)
+                dW.copy_(hW, non_blocking=True)
+                y = torch._scaled_mm(dA.view(torch.float8_e4m3fn), dW.view(torch.float8_e4m3fn).t(), inv_a, inv_w, None, None,
+                                     torch.bfloat16)
+                hC.copy_(y, non_blocking=True)
+            h2d, d2h = hA.numel() + hW.numel(), hC.numel() * 2
+            call = ("fp8_mps_patch.install(); torch._scaled_mm(A8, W8.t(), scale_a, scale_b, None, None, torch.bfloat16): A and W "
+                    "copied from pinned host memory, C copied back, every call")
+        else:
+            lin = lins[0]
+            hW = lin.weight.cpu().pin_memory()
+            r0_, r1_ = rank * M // n_gpus, (rank + 1) * M // n_gpus
+            hC = torch.empty(r1_ - r0_, N, dtype=torch.bfloat16).pin_memory()
 
-        e2e_steps = max(args.steps, 3)
-        for _ in range(max(args.warmup, 3)):
+            def e2e_step():
+                dA.copy_(hA, non_blocking=True)
+                lin.weight.copy_(hW, non_blocking=True)
+                y = lin(dA, inv_a, torch.bfloat16, mode="push")
+                hC.copy_(y[r0_:r1_], non_blocking=True)
+            h2d, d2h = hA.numel() + hW.numel(), hC.numel() * 2
+            call = ("ShardedScaledMM(W8, scale_b)(A8, scale_a, torch.bfloat16, mode='push'): A and this rank's W shard copied "
+                    "from pinned host memory, this rank's 1/N row slab of the assembled (M,N) result copied back, every call")
+        for _ in range(3):
             e2e_step()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        n0 = L.fp8b_launch_count()
+            torch.cuda.synchronize()
+        nl0 = L.fp8b_launch_count()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(e2e_steps):
+        for _ in range(e2e_steps * SETS):
             e2e_step()
         e1.record()
         torch.cuda.synchronize()
-        e2e_launches = L.fp8b_launch_count() - n0
-        e2e_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1))
-        e2e_val = n_gpus * C2_BYTES * e2e_steps / (e2e_ms * 1e-3) / 1e9
-        # second reading of "host buffers": the plug-in's deployment shape -- FP8 weights were moved to the GPU once
-        # (fp8_mps_patch scenario 1), only the activation comes from / the result goes to the host every step
-        w8 = Ws[0].view(torch.float8_e4m3fn).t()
+        e2e_launches = L.fp8b_launch_count() - nl0
+        if dist is not None:
+            dist.barrier()
+        e2e_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1)) / e2e_steps           # per step of SETS calls
+        e2e = {"value": round(C4_FLOPS * SETS / (e2e_ms * 1e-3) / 1e12, 3), "unit": "TFLOP/s",
+               "h2d_bytes_per_step": int(h2d * SETS), "d2h_bytes_per_step": int(d2h * SETS),
+               "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps, "calls_per_step": SETS, "call": call,
+               "kernel_launches": int(e2e_launches), "host_numa": numa,
+               "pcie_gbs_per_gpu": round((h2d + d2h) * SETS / (e2e_ms * 1e-3) / 1e9, 1)}
+        if n_gpus == 1:
+            w8 = w.view(torch.float8_e4m3fn).t()
 
-        def e2e_step_resident():
-            dx.copy_(hx, non_blocking=True)
-            y = torch._scaled_mm(dx.view(torch.float8_e4m3fn), w8, sa_d, sb_d, None, None, torch.bfloat16)
-            hout.copy_(y, non_blocking=True)
-
-        for _ in range(max(args.warmup, 3)):
-            e2e_step_resident()
-        torch.cuda.synchronize()
-        r0 = torch.cuda.Event(enable_timing=True)
-        r1 = torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(e2e_steps * 8):
-            e2e_step_resident()
-        r1.record()
-        torch.cuda.synchronize()
-        res_ms = max_over_ranks(torch, dist, r0.elapsed_time(r1)) / (e2e_steps * 8)
-        e2e = {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": int(hx.numel() + hW.numel()),
-               "resident_weights": {"value": round(n_gpus * C2_BYTES / (res_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
-                                    "ms_per_step": round(res_ms, 4), "h2d_bytes_per_step": int(hx.numel()),
-                                    "d2h_bytes_per_step": int(hout.numel() * 2),
-                                    "note": "weights already on the GPU (moved once, as the plug-in does); x copied in and y "
-                                            "copied out every step through the patched torch._scaled_mm; L2-warm (one weight)"},
-               "d2h_bytes_per_step": int(hout.numel() * 2), "ms_per_step": round(e2e_ms / e2e_steps, 4),
-               "steps": e2e_steps, "call": "torch._scaled_mm after fp8_mps_patch.install(); one GEMV per step; "
-               "x and W copied from pinned host memory and the result read back every step",
-               "kernel_launches": int(e2e_launches)}
+            def e2e_resident():
+                dA.copy_(hA, non_blocking=True)
+                y = torch._scaled_mm(dA.view(torch.float8_e4m3fn), w8, inv_a, inv_w, None, None, torch.bfloat16)
+                hC.copy_(y, non_blocking=True)
+            for _ in range(3):
+                e2e_resident()
+            torch.cuda.synchronize()
+            r0 = torch.cuda.Event(enable_timing=True)
+            r1 = torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(e2e_steps * SETS):
+                e2e_resident()
+            r1.record()
+            torch.cuda.synchronize()
+            res_ms = r0.elapsed_time(r1) / (e2e_steps * SETS)
+            e2e["resident_weights"] = {"value": round(C4_FLOPS / (res_ms * 1e-3) / 1e12, 3), "unit": "TFLOP/s",
+                                       "ms_per_call": round(res_ms, 4), "h2d_bytes_per_call": int(hA.numel()),
+                                       "d2h_bytes_per_call": int(hC.numel() * 2),
+                                       "note": "the plug-in's deployment shape: FP8 weights moved to the GPU once"}
     finally:
         fp8_mps_patch.uninstall()
 
     line = {
-        "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": n_gpus, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 _scaled_mm GEMV M=1 K=14336 N=4096, per-tensor scales, bf16 out "
-                               "(BASELINE.json configs[1])",
-                   "step": f"{calls} GEMV calls = {PASSES} passes over {ROTATION} distinct weight matrices, one CUDA graph",
-                   "l2": f"inputs larger than L2: {ROTATION} x 58.7 MB weight rotation (940 MB) per pass",
-                   "algorithmic_bytes_per_call": C2_BYTES, "parallelism": "replicas" if n_gpus > 1 else "single-gpu",
-                   "arith": "e4m3 operands, exact fp16 products, fp32 accumulation (FHFMA)"},
-        "roofline": {"bound": "hbm", "achieved": round(per_gpu, 1), "peak": peaks["hbm"], "unit": "GB/s",
-                     "frac": round(per_gpu / peaks["hbm"], 4), "traffic": profile_traffic("gemv"),
-                     "frac_of_nominal_8000": round(per_gpu / 8000.0, 4), "us_per_launch": round(us_per_call, 3),
-                     "peak_source": f"{peaks['source']} copy bandwidth (MEASURED_PEAKS.json)",
-                     "kernel": "fp8_gemv_kernel<1,4>",
-                     "read_kernel_floor": "a plain 16-byte-load read kernel moves the same 58.7 MB in 12.35 us on this GPU "
-                                          "(profiles/tools/membw.cu): ~4.3 us of fixed ramp/drain per launch + 7.3 TB/s streaming"},
-        "static_weights_pdl": {"value": round(n_gpus * C2_BYTES * calls / (ms_static / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
-                               "us_per_launch": round(ms_static / args.steps * 1e3 / calls, 3),
-                               "note": "opt-in FP8B_OPT_STATIC_WEIGHTS=1: consecutive GEMVs overlap via programmatic dependent launch"},
-        "four_streams": {"value": round(n_gpus * C2_BYTES * calls / (ms_streams / args.steps * 1e-3) / 1e9, 1), "unit": "GB/s",
-                         "frac": round(C2_BYTES * calls / (ms_streams / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
-                         "note": "the same 128 independent calls issued round-robin on 4 forked streams inside the graph: "
-                                 "ramp-up and drain of neighbouring launches overlap (not the headline: a decode chain is serial)"},
-        "batched_gemv": batched,
+        "metric": METRIC, "value": round(value, 1), "unit": "TFLOP/s", "n_gpus": n_gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_for(n_gpus),
+        "roofline": {"bound": "tensor", "achieved": round(per_gpu, 1), "peak": round(fp8_peak, 1), "unit": "TFLOP/s",
+                     "frac": round(per_gpu / fp8_peak, 4), "traffic": profile_traffic("gemm") if n_gpus == 1 else None,
+                     "frac_of_nominal_4500": round(per_gpu / 4500.0, 4), "us_per_launch": round(kernel_us, 2),
+                     "peak_source": f"{peaks['source']}: 2 x bf16 cuBLAS burst (MEASURED_PEAKS.json) as the dense-FP8 proxy",
+                     "kernel": kernel_name, "flops_per_launch": C4_FLOPS // n_gpus},
         "e2e": e2e,
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(launches_per_step * steps),
         "clocks": clocks,
     }
+    if sharded is not None:
+        line["sharded"] = sharded
 
-    # ---------------- the other BASELINE configs
-    if not args.no_sub:
+    # ---------------- the other BASELINE configs (single-GPU paths: casts and GEMVs are replicas-only)
+    if not args.no_sub and n_gpus == 1:
         sub = {}
+        gen = torch.Generator(device=dev).manual_seed(1)
+        sub["C4_library_yardstick"] = bench_library_yardstick(torch, bufs, steps, warmup)
+        if "us_per_call" in sub["C4_library_yardstick"]:
+            sub["C4_library_yardstick"]["ours_over_library"] = round(sub["C4_library_yardstick"]["us_per_call"] / us_per_call, 3)
+        try:
+            L.fp8b_set_option(20, 2)              # FP8B_OPT_TUNE_GEMM_STORE = 2: same kernel with the TMA-store epilogue
+            ms_t, _, _, _ = time_graph(torch, step_single, steps, warmup)
+            sub["C4_tma_store_epilogue"] = {"us_per_call": round(ms_t / steps * 1e3 / SETS, 2)}
+        except Exception as e:
+            sub["C4_tma_store_epilogue"] = {"error": repr(e)[:200]}
+        finally:
+            L.fp8b_set_option(20, -1)
+        del bufs
+        torch.cuda.empty_cache()
+        try:
+            sub["C2_gemv_M1_K14336_N4096_bf16"] = bench_c2(torch, L, gen, dev, peaks, steps, warmup)
+        except Exception as e:
+            sub["C2_error"] = repr(e)[:300]
         try:
             sub["C1_gemv_M1_K4096_N4096_f16"] = bench_gemv_cfg(torch, L, C1, C1_BYTES, torch.float16, False, gen, dev,
-                                                               peaks, args.steps, args.warmup, rotation=32)
+                                                               peaks, steps, warmup, rotation=32)
             sub["C3_gemv_M4_K4096_N4096_bias_bf16"] = bench_gemv_cfg(torch, L, C3, C3_BYTES, torch.bfloat16, True, gen,
-                                                                     dev, peaks, args.steps, args.warmup, rotation=32)
+                                                                     dev, peaks, steps, warmup, rotation=32)
             sub["C1_gemv_M1_K4096_N4096_f16"]["roofline"]["traffic"] = profile_traffic("gemv1k4")
             sub["C3_gemv_M4_K4096_N4096_bias_bf16"]["roofline"]["traffic"] = profile_traffic("gemv4")
+            sq = bench_gemv_cfg(torch, L, SQ, SQ_BYTES, torch.float32, False, gen, dev, peaks, steps, warmup, rotation=4)
+            sq["reference_published"] = "2.38 ms on Apple M4 Pro (README.md:80; test_fp8_metal.py:232-236), other hardware"
+            sub["ref_bench_gemv_M1_K14336_N14336_f32"] = sq
         except Exception as e:
-            sub["gemv_error"] = repr(e)
+            sub["gemv_error"] = repr(e)[:300]
         try:
-            s2 = ClockSampler(torch.cuda.current_device())
-            s2.start()
-            tg0 = time.perf_counter()
-            shard = C4["N"] // n_gpus if n_gpus > 1 else None
-            res, bufs = bench_gemm_c4(torch, L, gen, dev, peaks, args.steps, args.warmup, n_shard=shard)
-            res["clocks"] = s2.summary(tg0, time.perf_counter())
-            s2.stop()
-            key = "C4_gemm_M4096_K3072_N12288_bf16" + (f"_shard{n_gpus}" if n_gpus > 1 else "")
-            if n_gpus == 1:
-                res["roofline"]["traffic"] = profile_traffic("gemm")
-            sub[key] = res
-            if dist is not None:
-                from fp8_sharded import ShardedScaledMM
-                a, inv_a, w, inv_w, c_local = bufs
-                lin = ShardedScaledMM(w, inv_w, None, weight_is_shard=True, full_N=C4["N"])
-                variants = {
-                    "allgather_rank_major": lambda: lin(a, inv_a, torch.bfloat16, layout="rank_major"),
-                    "allgather_row_major": lambda: lin(a, inv_a, torch.bfloat16, layout="row_major"),
-                    "multicast_fused": lambda: lin(a, inv_a, torch.bfloat16, mode="multicast"),
-                    "peer_store_fused": lambda: lin(a, inv_a, torch.bfloat16, mode="peers"),
-                }
-                comp_us = max_over_ranks(torch, dist, res["us_per_call"])
-                sh = {"world": n_gpus, "compute_only_us_max_rank": round(comp_us, 2),
-                      "compute_only_tflops_total": round(C4_FLOPS / (comp_us * 1e-6) / 1e12, 1),
-                      "exchange_recv_bytes_per_gpu": int((n_gpus - 1) * C4["M"] * shard * 2)}
-                for name, fn in variants.items():
-                    try:
-                        for _ in range(max(args.warmup, 3)):
-                            fn()
-                        torch.cuda.synchronize()
-                        dist.barrier()
-                        torch.cuda.synchronize()
-                        e0 = torch.cuda.Event(enable_timing=True)
-                        e1 = torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        for _ in range(args.steps):
-                            fn()
-                        e1.record()
-                        torch.cuda.synchronize()
-                        t_us = max_over_ranks(torch, dist, e0.elapsed_time(e1)) / args.steps * 1e3
-                        sh[name] = {"us": round(t_us, 2), "tflops_total": round(C4_FLOPS / (t_us * 1e-6) / 1e12, 1)}
-                    except Exception as e:
-                        sh[name] = {"error": repr(e)[:200]}
-                sh["layouts"] = {"allgather_rank_major": "[world, M, N/world], no re-layout pass",
-                                 "allgather_row_major": "(M, N) contiguous, one extra device pass",
-                                 "peer_store_fused": "(M, N) row-major on every rank, written by the GEMM epilogue with plain "
-                                                     "stores into every rank's symmetric buffer (own shard stays local)",
-                                 "multicast_fused": "(M, N) row-major on every rank, written by the GEMM epilogue through "
-                                                    "the NVSwitch multicast mapping; double-buffered, one symmetric-memory barrier per call"}
-                sub[key]["sharded"] = sh
-            del bufs
+            sub["C5_casts_flux_12B"] = bench_casts_c5(torch, L, gen, dev, peaks, steps, warmup)
         except Exception as e:
-            sub["gemm_error"] = repr(e)
-        try:
-            if rank == 0:
-                sub["C5_casts_flux_12B"] = bench_casts_c5(torch, L, gen, dev, peaks, args.steps, args.warmup)
-        except Exception as e:
-            sub["cast_error"] = repr(e)
+            sub["cast_error"] = repr(e)[:300]
         line["sub"] = sub
+    elif n_gpus > 1:
+        line["sub_note"] = "C1/C2/C3/C5 are single-GPU paths (replicas only, SURVEY 8e): see the N=1 line"
 
     sampler.stop()
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_gemv_baseline()
+            line["cpu_baseline"] = cpu_c4_baseline()
         except Exception as e:
             line["cpu_baseline"] = {"error": repr(e)}
     if dist is not None:

@@ -11,6 +11,7 @@
 // waitUntilCompleted (fp8_bridge.cpp:180-185,244-245), this one passes device pointers and the
 // caller's current CUDA stream and returns without synchronising.  No CUDA kernel lives here and
 // nothing falls back to ATen math: every op is one or two calls into the C ABI.
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <torch/extension.h>
@@ -144,7 +145,17 @@ bool is_fp8_like(const torch::Tensor& t)
 const float* scale_ptr(const c10::optional<torch::Tensor>& s, const torch::Device& dev, torch::Tensor& keep, int64_t& len)
 {
     if (!s.has_value() || !s->defined()) {
-        keep = torch::ones({1}, torch::TensorOptions().dtype(torch::kFloat32).device(dev));   // fp8_mps_patch.py:87-90
+        // default scale 1.0 (fp8_mps_patch.py:87-90): one cached tensor per device instead of an allocation and a fill
+        // kernel on every call
+        static std::mutex mu;
+        static torch::Tensor ones[64];
+        const int idx = dev.has_index() ? dev.index() : 0;
+        std::lock_guard<std::mutex> lock(mu);
+        if (idx < 0 || idx >= 64) keep = torch::ones({1}, torch::TensorOptions().dtype(torch::kFloat32).device(dev));
+        else {
+            if (!ones[idx].defined()) ones[idx] = torch::ones({1}, torch::TensorOptions().dtype(torch::kFloat32).device(dev));
+            keep = ones[idx];
+        }
     } else if (s->device() == dev && s->scalar_type() == at::kFloat && s->is_contiguous()) {
         keep = *s;
     } else {

@@ -225,7 +225,10 @@ extern "C" int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B,
     if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
     const size_t need = fp8b_linear_dynamic_workspace_bytes(M, K);
     const bool have_ws = workspace && workspace_bytes >= need && aligned(workspace, 16);
-    if (M <= 16 && (K < 16 || (K % 16) != 0 || !aligned(B, 16) || !aligned(X, 16))) return FP8B_ERR_UNSUPPORTED;
+    // the single-kernel plan reads X and B with 16-byte vectors; the workspace plan (quantise rows, then the GEMV
+    // dispatcher) takes any K and alignment through their scalar / generic kernels
+    const bool vec_ok = K >= 16 && (K % 16) == 0 && aligned(B, 16) && aligned(X, 16);
+    if (M <= 16 && !have_ws && !vec_ok) return FP8B_ERR_UNSUPPORTED;
     if (M > 16 && !have_ws) return FP8B_ERR_UNSUPPORTED;         // the GEMM path always quantises into the workspace
     MMArgs a;
     a.A = nullptr; a.B = B; a.C = C; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
@@ -242,7 +245,7 @@ extern "C" int fp8b_linear_dynamic(const void* X, int x_dtype, const uint8_t* B,
     // scale_a.  Converting inside the GEMM's producer stage instead would redo the encode once per N-tile
     // column (48x for C4) on data that is read from L2 anyway; one 6 us pass over A is cheaper.
     const int plan = tune(kTuneDynamicPlan, 0);         // 1 = force single kernel, 2 = force chain
-    if (have_ws && (plan != 1 || M > 16)) {
+    if (have_ws && (plan != 1 || M > 16 || !vec_ok)) {
         uint8_t* q = static_cast<uint8_t*>(workspace);
         float* inv = inv_scale_a_out ? inv_scale_a_out
                                      : reinterpret_cast<float*>(q + align16((size_t)M * (size_t)K));

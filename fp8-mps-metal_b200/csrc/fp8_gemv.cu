@@ -494,6 +494,8 @@ static int launch_gemv_xq_mt(const GemvXqParams& xp, int S, size_t smem, cudaStr
 
 int launch_gemv_fhfma(const MMArgs& a, const Epi& epi, const void* X, int x_dtype, float* inv_scale_out);
 
+constexpr bool kGemvRingDefault = false;     // measured choice, see DESIGN.md 3.2
+
 int launch_gemv(const MMArgs& a)
 {
     if (!gemv_supported(a)) return FP8B_ERR_UNSUPPORTED;
@@ -507,6 +509,8 @@ int launch_gemv(const MMArgs& a)
                                                                                              a.a_fmt, a.b_fmt);
         return after_launch();
     }
+    // impl 4 (and the default where it applies): the persistent TMA-ring kernel, one design for M = 1..16
+    if ((impl == 4 || (impl == 0 && kGemvRingDefault)) && !a.chain_pdl && gemv_ring_supported(a)) return launch_gemv_ring(a);
     if (gemv_mma_supported(a) && (impl == 2 || (impl == 0 && a.M >= 2))) return launch_gemv_mma(a);
     if (gemv_rows_supported(a) && (impl == 3)) return launch_gemv_rows(a);
     const Epi epi = make_epi(a);

@@ -96,6 +96,15 @@ def _same_accel_device(tensor, device):
 # --------------------------------------------------------------------------- _scaled_mm
 
 _SCALED_MM_POSITIONAL = ("scale_a", "scale_b", "bias", "scale_result", "out_dtype", "use_fast_accum")
+_FP8_LIKE = frozenset(d for d in (torch.uint8, _E4M3, _E5M2) if d is not None)     # fp8_mps_patch.py:64-65
+_scaled_mm_patch_fn = None
+
+
+def _bind_kernel():
+    """Resolve the extension's scaled_mm_patch once (the import is lazy, like the reference's, fp8_mps_patch.py:74)."""
+    global _scaled_mm_patch_fn
+    _scaled_mm_patch_fn = _kernels()._get_lib().scaled_mm_patch       # the extension function itself, no Python layer between
+    return _scaled_mm_patch_fn
 
 
 def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=None, bias=None,
@@ -109,23 +118,33 @@ def _metal_scaled_mm(input, other, *args, out_dtype=None, scale_a=None, scale_b=
     Result: ((sum_k a*b) * scale_a) * scale_b [+ bias] [* scale_result], cast to out_dtype
             (float32 when out_dtype is None, fp8_mps_patch.py:103-104).
     """
+    # Hot path first, with as little Python as possible (a decode GEMV runs 5-12 us on the GPU; this wrapper is
+    # called once per linear layer): FP8 operands on the accelerator go straight to ONE extension call.
+    if input.is_cuda and input.dtype in _FP8_LIKE and other.dtype in _FP8_LIKE:
+        n = len(args)
+        if n:                                          # aten schema order: scale_a, scale_b, bias, scale_result, out_dtype
+            if n > len(_SCALED_MM_POSITIONAL):
+                raise TypeError(f"_scaled_mm() takes at most {2 + len(_SCALED_MM_POSITIONAL)} positional arguments")
+            scale_a = args[0]
+            if n > 1:
+                scale_b = args[1]
+                if n > 2:
+                    bias = args[2]
+                    if n > 3:
+                        scale_result = args[3]
+                        if n > 4:
+                            out_dtype = args[4]
+        # dtype views, the (N,K) view of `other`, default scales (fp8_mps_patch.py:82-90) and the fused epilogue
+        # (:95-104) all happen inside that call.  float8_e5m2 operands are decoded as e5m2; uint8 is taken as e4m3fn.
+        return (_scaled_mm_patch_fn or _bind_kernel())(input, other, scale_a, scale_b, bias, scale_result, out_dtype)
+
     kw = dict(out_dtype=out_dtype, scale_a=scale_a, scale_b=scale_b, bias=bias,
               scale_result=scale_result, use_fast_accum=use_fast_accum)
     if len(args) > len(_SCALED_MM_POSITIONAL):
         raise TypeError(f"_scaled_mm() takes at most {2 + len(_SCALED_MM_POSITIONAL)} positional arguments")
     for name, value in zip(_SCALED_MM_POSITIONAL, args):      # aten schema order
         kw[name] = value
-
-    on_accel = input.device.type == ACCEL
-    fp8_like = (torch.uint8, _E4M3, _E5M2)           # the reference's predicate (fp8_mps_patch.py:64-65)
-    is_fp8 = input.dtype in fp8_like and other.dtype in fp8_like
-    if not (on_accel and is_fp8):
-        return _original_scaled_mm(input, other, **kw)
-    # dtype views, the (N,K) view of `other`, default scales (fp8_mps_patch.py:82-90) and the fused epilogue
-    # (:95-104) all happen inside one extension call: the Python-level version of this cost more host time than
-    # a decode GEMV takes on the GPU.  float8_e5m2 operands are decoded as e5m2; uint8 is taken as e4m3fn.
-    return _kernels().scaled_mm_patch(input, other, kw["scale_a"], kw["scale_b"], kw["bias"], kw["scale_result"],
-                                      kw["out_dtype"])
+    return _original_scaled_mm(input, other, **kw)             # not FP8-on-accelerator: the reference's predicate (:64-65)
 
 
 # --------------------------------------------------------------------------- Tensor.to

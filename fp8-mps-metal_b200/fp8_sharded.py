@@ -64,6 +64,7 @@ class ShardedScaledMM:
             self.N = int(full_N)
         else:
             self.N = int(weight_u8.shape[0])
+        self.align = align
         self.n0, self.n1, self.width = shard_bounds(self.N, self.world, self.rank, align)
         if weight_is_shard:
             assert weight_u8.shape[0] == self.n1 - self.n0
@@ -152,12 +153,14 @@ class ShardedScaledMM:
         odt = out_dtype or torch.float32
         if self.world == 1:
             return self.local(x_u8, scale_a, out_dtype)
+        if not self.fused_supported("multicast", M, x_u8.shape[1], odt, x_u8.device):
+            raise RuntimeError("multicast mode needs N/world % 32 == 0 and 16-byte aligned shard columns on every rank")
         key, pair, turn = self._symm_buffers(M, odt, x_u8.device)
         buf, hdl = pair[turn]
-        self._symm = (key, pair, turn ^ 1)
         mc = getattr(hdl, "multicast_ptr", 0)
-        if not mc:
+        if not mc:                                              # a property of the system: every rank raises alike
             raise RuntimeError("symmetric memory has no multicast mapping on this system (NVLS unavailable)")
+        self._symm = (key, pair, turn ^ 1)
         if self.n1 > self.n0:
             fp8_mps_native._get_lib().fp8_scaled_mm_multicast(
                 x_u8, self.weight, scale_a, self.scale_b, self.bias, odt, int(mc), int(self.N), int(self.n0))
@@ -173,18 +176,15 @@ class ShardedScaledMM:
         odt = out_dtype or torch.float32
         if self.world == 1:
             return self.local(x_u8, scale_a, out_dtype)
+        if not self.fused_supported("peers", M, x_u8.shape[1], odt, x_u8.device):   # same verdict on every rank, before any barrier
+            raise RuntimeError("peer-store mode needs M > 128 and, on every rank, N/world > 128, N/world % 32 == 0")
         key, pair, turn = self._symm_buffers(M, odt, x_u8.device)
         buf, hdl = pair[turn]
         self._symm = (key, pair, turn ^ 1)
         deltas = self._peer_deltas(turn, buf, hdl)
         if self.n1 > self.n0:
-            try:
-                fp8_mps_native._get_lib().fp8_scaled_mm_peers(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
-                                                              deltas, int(self.n0))
-            except RuntimeError as e:
-                if "unsupported" not in str(e):
-                    raise
-                raise RuntimeError("peer-store mode needs M > 128, N/world > 128 and 16-byte aligned shards: " + str(e))
+            fp8_mps_native._get_lib().fp8_scaled_mm_peers(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
+                                                          deltas, int(self.n0))
         hdl.barrier(channel=0)                                  # every rank's tiles have landed everywhere
         return buf
 
@@ -200,7 +200,30 @@ class ShardedScaledMM:
             cache[1][turn] = torch.tensor([p - local for p in ptrs], dtype=torch.int64, device=buf.device)
         return cache[1][turn]
 
-    # ------------------------------------------------------------------ fused TMA-store path
+    # ------------------------------------------------------------------ which fused plans can serve a call
+    def fused_supported(self, mode: str, M: int, K: int, odt, device) -> bool:
+        """Whether a fused plan can serve this call ON EVERY RANK -- computed from (mode, M, K, N, world, dtype)
+        only, over all ranks' shard bounds, so every rank reaches the same verdict without communicating.  (Round 1
+        checked per rank inside the launch: with N = 4080, w = 2 one rank launched and waited in the barrier while
+        the other raised.)"""
+        if mode == "push":
+            return self.push_supported(M, K, odt, device)
+        if self.world <= 1 or device.type != "cuda" or not dist.is_initialized() or dist.get_backend(self.group) != "nccl":
+            return False
+        esz = torch.empty((), dtype=odt).element_size()
+        if K < 16 or K % 16 or (self.N * esz) % 16:
+            return False
+        for r in range(self.world):
+            n0, n1, _ = shard_bounds(self.N, self.world, r, self.align)
+            nl = n1 - n0
+            if nl == 0:
+                continue
+            if nl % 32 or (n0 * esz) % 16:                       # multimem.st / st.global.v4 have no sub-word form
+                return False
+            if mode == "peers" and not (M > 128 and nl > 128):   # CTA-pair tile configurations only
+                return False
+        return mode in ("peers", "multicast")
+
     def push_supported(self, M: int, K: int, odt, device) -> bool:
         """Whether mode="push" can serve this call -- evaluated from (M, K, N, world, dtype) only, so every rank
         reaches the same answer without communicating (a rank must never skip the closing barrier)."""
@@ -228,12 +251,23 @@ class ShardedScaledMM:
         buf, hdl = pair[turn]
         self._symm = (key, pair, turn ^ 1)
         if self.n1 > self.n0:
-            ptrs = [int(p) for p in hdl.buffer_ptrs]
-            order = [ptrs[(self.rank + d) % self.world] for d in range(self.world)]     # own buffer first, then the ring of peers
             fp8_mps_native._get_lib().fp8_scaled_mm_push(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
-                                                         order, int(self.n0))
+                                                         self._push_order(turn, hdl), int(self.n0))
         hdl.barrier(channel=0)                                  # every rank's boxes have landed everywhere
         return buf
+
+    def _push_order(self, turn, hdl):
+        """Destination base addresses for this buffer of the pair: own buffer first, then the ring of peers starting
+        at rank+1, so that at any moment the ranks write to different destinations."""
+        cache = getattr(self, "_order", None)
+        if cache is None or cache[0] is not self._symm[1]:
+            cache = (self._symm[1], {})
+            self._order = cache
+        if turn not in cache[1]:
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            assert len(ptrs) == self.world
+            cache[1][turn] = [ptrs[(self.rank + d) % self.world] for d in range(self.world)]
+        return cache[1][turn]
 
     def best_mode(self, M: int = 0, K: int = 0, odt=torch.bfloat16, device=None) -> str:
         """The fused TMA-store plan whenever it applies (decided from the shape alone, identically on every rank),

@@ -20,7 +20,11 @@ lin = ShardedScaledMM(w, sb, None, weight_is_shard=True, full_N=N)
 variants = {"compute_only": lambda: lin.local(a, sa, torch.bfloat16),
             "allgather_rank_major": lambda: lin(a, sa, torch.bfloat16, layout="rank_major"),
             "multicast_fused": lambda: lin(a, sa, torch.bfloat16, mode="multicast"),
-            "peer_store_fused": lambda: lin(a, sa, torch.bfloat16, mode="peers")}
+            "peer_store_fused": lambda: lin(a, sa, torch.bfloat16, mode="peers"),
+            "push_fused": lambda: lin(a, sa, torch.bfloat16, mode="push")}
+only = os.environ.get("ONLY")
+if only:
+    variants = {k: v for k, v in variants.items() if k in only.split(",")}
 out = {}
 for name, fn in variants.items():
     try:
@@ -35,6 +39,14 @@ for name, fn in variants.items():
         out[name] = round(float(t.item()), 1)
     except Exception as e:
         out[name] = repr(e)[:120]
+# parity of the push plan against the all-gather of the same shards
+try:
+    y_push = lin(a, sa, torch.bfloat16, mode="push").clone()
+    y_ag = lin(a, sa, torch.bfloat16, layout="row_major")
+    torch.cuda.synchronize()
+    out["push==allgather"] = bool(torch.equal(y_push, y_ag))
+except Exception as e:
+    out["push==allgather"] = repr(e)[:200]
 if rank == 0:
     print(f"world {world}: " + "  ".join(f"{k} {v} us" for k, v in out.items()), flush=True)
 dist.barrier()

@@ -5,7 +5,7 @@
         tests/mgpu_sharded.py
 
 Every rank compares (a) the NCCL all-gather path, row-major and rank-major layouts, and (b) the fused
-multicast-store and peer-store paths against the un-sharded GEMM it computes locally with the same kernel, and a slab of
+multicast-store, peer-store and TMA-push paths against the un-sharded GEMM it computes locally with the same kernel, and a slab of
 the result against the CPU oracle.  Prints one PASS/FAIL line per rank; exit code 0 only if all pass."""
 import os
 import sys
@@ -76,6 +76,24 @@ def main():
             except Exception as e:
                 pe_state = f"FAILED: {type(e).__name__}: {str(e)[:160]}"
                 ok = False
+        pu_state = "skipped"
+        if lin.push_supported(M, K, torch.bfloat16, dev):
+            try:
+                ypu = lin(Ad, sad, out_dtype=torch.bfloat16, mode="push")
+                torch.cuda.synchronize()
+                pu_ok = bool(torch.equal(ypu, full))
+                ypu2 = lin(Ad, sad, out_dtype=torch.bfloat16, mode="push")           # the other buffer of the pair
+                ypu3 = lin(Ad, sad, out_dtype=torch.bfloat16, mode="auto")           # auto = push; buffer reuse
+                torch.cuda.synchronize()
+                pu_ok = pu_ok and bool(torch.equal(ypu2, full)) and bool(torch.equal(ypu3, full))
+                pu_state = "ok" if pu_ok else "MISMATCH"
+                ok = ok and pu_ok
+            except Exception as e:
+                pu_state = f"FAILED: {type(e).__name__}: {str(e)[:160]}"
+                ok = False
+        else:
+            ok = False
+            pu_state = "UNSUPPORTED (unexpected for these shapes)"
         rows = slice(0, min(M, 128))
         ref = o.scaled_mm(A[rows].numpy(), W.numpy(), sa.numpy(), sb.numpy(),
                           None if bias is None else bias.float().numpy(), None, "bf16", accum="f32")
@@ -83,7 +101,7 @@ def main():
         case_ok = same and same_rank and err <= 3e-3
         ok = ok and case_ok
         msgs.append(f"M{M} K{K} N{N}: allgather={'ok' if same else 'MISMATCH'} rank_major={'ok' if same_rank else 'MISMATCH'} "
-                    f"multicast={mc_state} peers={pe_state} oracle_rel_rmse={err:.2e}")
+                    f"multicast={mc_state} peers={pe_state} push={pu_state} oracle_rel_rmse={err:.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     for m in msgs:

@@ -57,7 +57,14 @@ def _worker(rank, world, port, N, per_row, with_bias, results):
                                None if bias is None else torch.from_numpy(bias[n0:n1].copy()), mm_fn=_oracle_mm,
                                weight_is_shard=True, full_N=N)
         y2 = lin2(torch.from_numpy(A), torch.from_numpy(sa), out_dtype=torch.float32)
-        results[rank] = ok_row and bool(ok_rank) and bool(np.array_equal(y2.numpy(), ref))
+        # mode="auto" on a gloo / CPU group: the fused plans do not apply, every rank must fall back to all-gather
+        # (and reach that verdict identically -- ADVICE r1: a rank that raises while its peer waits in a barrier hangs the job)
+        cpu = torch.device("cpu")
+        ok_auto = lin.best_mode(M, K, torch.float32, cpu) == "allgather"
+        ok_auto = ok_auto and not any(lin.fused_supported(m, M, K, torch.float32, cpu) for m in ("push", "peers", "multicast"))
+        y3 = lin(torch.from_numpy(A), torch.from_numpy(sa), out_dtype=torch.float32, mode="auto")
+        ok_auto = ok_auto and bool(np.array_equal(y3.numpy(), ref))
+        results[rank] = ok_row and bool(ok_rank) and bool(np.array_equal(y2.numpy(), ref)) and ok_auto
     finally:
         dist.destroy_process_group()
 
@@ -84,3 +91,37 @@ def test_shard_bounds_cover_and_align():
                 cover += list(range(n0, n1))
             assert cover == list(range(N))
     assert shard_bounds(12288, 8, 3) == (4608, 6144, 1536)
+
+
+def test_fused_plan_support_is_rank_independent():
+    """The verdict "can the fused plan serve this call" must be the same on every rank: it is computed over ALL
+    ranks' shard bounds.  N = 4080, w = 2 splits into 2048 + 2032 columns -- round 1 launched on rank 0 and raised on
+    rank 1 (2032 % 32 != 0), leaving rank 0 in the barrier."""
+    sys.path.insert(0, os.path.join(ROOT, "fp8-mps-metal_b200"))
+    import fp8_sharded
+    from fp8_sharded import ShardedScaledMM
+
+    class FakeDist:                                  # stands in for an initialised NCCL group of `world` ranks
+        def __init__(self, world, rank): self.world, self.rank = world, rank
+        def is_initialized(self): return True
+        def get_world_size(self, group=None): return self.world
+        def get_rank(self, group=None): return self.rank
+        def get_backend(self, group=None): return "nccl"
+
+    real = fp8_sharded.dist
+    cuda = torch.device("cuda", 0)
+    try:
+        for N, world, M, expect in [(4080, 2, 4096, {"push": True, "peers": False, "multicast": False}),
+                                    (12288, 8, 4096, {"push": True, "peers": True, "multicast": True}),
+                                    (12288, 8, 64, {"push": True, "peers": False, "multicast": True}),
+                                    (1000, 2, 300, {"push": True, "peers": False, "multicast": False}),
+                                    (1004, 2, 300, {"push": False, "peers": False, "multicast": False})]:
+            verdicts = []
+            for rank in range(world):
+                fp8_sharded.dist = FakeDist(world, rank)
+                lin = ShardedScaledMM(torch.zeros(N, 64, dtype=torch.uint8), torch.ones(1), mm_fn=lambda *a: None)
+                verdicts.append({m: lin.fused_supported(m, M, 64, torch.bfloat16, cuda) for m in ("push", "peers", "multicast")})
+                assert lin.best_mode(M, 64, torch.bfloat16, cuda) == ("push" if expect["push"] else "allgather")
+            assert all(v == expect for v in verdicts), (N, world, M, verdicts)
+    finally:
+        fp8_sharded.dist = real
