@@ -699,13 +699,10 @@ def pin_to_gpu_numa_node(torch, index):
     """Best effort: run this rank's host thread (and so first-touch its pinned buffers) on the CPUs of the NUMA node
     the GPU hangs off, so that N ranks' host<->device copies do not all cross one memory controller."""
     try:
-        prop_id = torch.cuda.get_device_properties(index).pci_bus_id
-        bus = f"0000:{prop_id:02x}:00.0" if isinstance(prop_id, int) else str(prop_id).lower()
+        pr = torch.cuda.get_device_properties(index)
+        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
         if not os.path.exists(f"/sys/bus/pci/devices/{bus}"):
-            import pynvml
-            pynvml.nvmlInit()
-            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
-            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+            return "pci device not visible in sysfs"
         node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
         if node < 0:
             return "numa node unknown"

@@ -25,8 +25,11 @@ import sysconfig
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libfp8_b200.so")
+# FP8B_BUILD_PROFILE=1: a second, PROFILING-ONLY library (extra kernel knobs compiled in) under profiles/tools/bin/;
+# the shipped libfp8_b200.so is never built with it.  Load it with FP8B_LIB=... in the profiling scripts.
+PROFILE = os.environ.get("FP8B_BUILD_PROFILE") == "1"
+OBJ = os.path.join(ROOT, "profiles", "tools", "bin", "obj") if PROFILE else os.path.join(HERE, "build")
+LIB = os.path.join(ROOT, "profiles", "tools", "bin", "libfp8_b200_profile.so") if PROFILE else os.path.join(HERE, "libfp8_b200.so")
 
 CU_SOURCES = ["fp8_cast.cu", "fp8_gemv.cu", "fp8_gemv_mma.cu", "fp8_gemv_rows.cu", "fp8_gemv_batch.cu", "fp8_gemv_ring.cu", "fp8_gemm_simt.cu", "fp8_gemm_tcgen05.cu", "fp8_capi.cu"]
 HEADERS = ["fp8_codec.cuh", "fp8_common.cuh", "fp8_mm.cuh", "fp8_async.cuh"]
@@ -87,13 +90,14 @@ def _run(cmd):
 
 def build_lib(force: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    sources = CU_SOURCES + (["fp8_prof.cu"] if PROFILE else [])
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(ROOT, "include", "fp8_b200.h")]
     nvcc = _nvcc()
     jobs = []
     objs = []
     stamps = []
     flags = NVCC_FLAGS + EXTRA_NVCC_FLAGS
-    for src in CU_SOURCES:
+    for src in sources:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
@@ -149,7 +153,7 @@ def build_ext(force: bool = False) -> str:
 
 def build_all(force: bool = False, ext: bool = True):
     out = [build_lib(force)]
-    if ext:
+    if ext and not PROFILE:
         out.append(build_ext(force))
     return out
 

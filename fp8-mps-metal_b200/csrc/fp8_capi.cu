@@ -46,7 +46,8 @@ int tune_int(const char* name, int dflt) { return env_int(name, dflt); }
 std::atomic<int> g_tune[kTuneCount];
 namespace {
 const char* const kTuneEnv[kTuneCount] = {"FP8B_GEMM_CFG", "FP8B_GEMV_IMPL", "FP8B_DYNAMIC_PLAN", "FP8B_CAST_SHAPE",
-                                          "FP8B_GEMM_STORE", "FP8B_GEMV_UNROLL", "FP8B_GEMV_BATCH", "FP8B_AMAX_CAP"};
+                                          "FP8B_GEMM_STORE", "FP8B_GEMV_UNROLL", "FP8B_GEMV_BATCH", "FP8B_AMAX_CAP",
+                                          "FP8B_GEMM_RASTER"};
 struct TuneInit {
     TuneInit() { for (int k = 0; k < kTuneCount; ++k) g_tune[k].store(env_int(kTuneEnv[k], -1)); }
 } g_tune_init;
@@ -315,5 +316,5 @@ extern "C" int fp8b_scaled_mm_push_supported(int out_dtype, int M, int N, int K,
 {
     if (M < 1 || N < 1 || K < 16 || (K % 16) != 0 || !valid_dtype(out_dtype) || ldc < N) return 0;
     if (!aligned(A, 16) || !aligned(B, 16) || !aligned(C, 16)) return 0;
-    return ((size_t)ldc * dtype_size(out_dtype)) % 16 == 0 ? 1 : 0;
+    return (((size_t)ldc * dtype_size(out_dtype)) % 16 == 0 && ((size_t)N * dtype_size(out_dtype)) % 16 == 0) ? 1 : 0;
 }

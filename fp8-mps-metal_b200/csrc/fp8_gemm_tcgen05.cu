@@ -47,9 +47,18 @@ constexpr int kEpiColSplits = kNumEpiWarps / 4;
 //              128-row x 128-byte box with cp.async.bulk.tensor (TMA store) to 1..8 destinations -- this rank's
 //              buffer and, over NVLink, the same place in every peer's buffer.  The epilogue warps never wait on
 //              the memory system, so the accumulator goes back to the MMA warp as soon as TMEM is drained.
-enum { kStDirect = 0, kStPeers = 1, kStTma = 2 };
+//   kStWide    kStTma with ONE box per tile and CTA: 128 rows x the whole tile width (16-bit outputs), linear in shared
+//              memory (SWIZZLE_NONE tensor map over 16-bit elements), so every row leaves as one 256- or 512-byte
+//              write instead of the 128 bytes a 128B-swizzled box allows.  NVLink moves 128-byte row segments at
+//              595 GB/s of the ~690 GB/s a peer accepts for contiguous writes (profiles/r2_scaling.md).  The epilogue's
+//              st.shared are then 8-way bank-conflicted -- ~256 cycles per tile, irrelevant next to a 9 000-cycle tile.
+//              (Also tried: one 1-D cp.async.bulk per 256-byte row -- 118 us against 98 us at w = 2: the TMA unit
+//              retires only about one bulk copy per 230 cycles.)
+enum { kStDirect = 0, kStPeers = 1, kStTma = 2, kStWide = 3 };
+template <int MODE> constexpr bool is_push() { return MODE == kStTma || MODE == kStWide; }
 constexpr int kMaxDst = 8;
-template <int MODE> constexpr int gemm_threads() { return 64 + 32 * kNumEpiWarps + (MODE == kStTma ? 32 : 0); }
+template <int MODE> constexpr int gemm_threads() { return 64 + 32 * kNumEpiWarps + (is_push<MODE>() ? 32 : 0); }
+
 constexpr int kStoreBoxBytes = 128 * 128;       // one TMA-store box: 128 rows x 128 bytes, 128B-swizzled
 constexpr int kStoreInflight = 2;               // TMA-store groups that may still be reading shared memory
 // Warp roles.  The epilogue takes the LOW warp ids and the two single-thread roles the HIGH ones: the warp
@@ -76,9 +85,10 @@ template <int BN, int CG, int MODE = kStDirect> struct GemmCfg {
     static constexpr int kBRows = BN / CG;                         // B rows staged by one CTA
     static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStoreSlots = 4;                          // kStTma: ring of TMA-store boxes
-    // epilogue staging: per epilogue warp 32 rows x 256 B, XOR-swizzled -- or the TMA-store ring
-    static constexpr int kEpiStageBytes = MODE == kStTma ? kStoreSlots * kStoreBoxBytes : kNumEpiWarps * 8192;
+    static constexpr int kSlotBytes = MODE == kStWide ? kBM * BN * 2 : kStoreBoxBytes;     // kStWide: 128 rows x BN 16-bit columns
+    static constexpr int kStoreSlots = MODE == kStWide ? (kSlotBytes <= 32768 ? 3 : 2) : 4; // ring of store boxes
+    // epilogue staging: per epilogue warp 32 rows x 256 B, XOR-swizzled -- or the store ring
+    static constexpr int kEpiStageBytes = is_push<MODE>() ? kStoreSlots * kSlotBytes : kNumEpiWarps * 8192;
     static constexpr int kStagesFit = (232448 - 1024 - 256 - kEpiStageBytes) / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;   // two accumulators; a power of two >= 32
@@ -95,11 +105,13 @@ struct StoreMaps { CUtensorMap m[kMaxDst]; };    // kStTma: one byte-typed map p
 struct NoStoreMaps { int unused; };
 template <int MODE> struct StoreMapsOf { using type = NoStoreMaps; };
 template <> struct StoreMapsOf<kStTma> { using type = StoreMaps; };
+template <> struct StoreMapsOf<kStWide> { using type = StoreMaps; };
 
 struct GemmParams {
     const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
+    int raster_n;                            // tile order: 0 = M fastest (consecutive work items share a B tile), 1 = N fastest
     int full_tiles;                          // work items [0, full_tiles) are BN-wide tiles ...
     int num_work;                            // ... items [full_tiles, num_work) are half-width tiles (last-wave split)
     Epi epi;
@@ -265,17 +277,17 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, 
 struct TileCoord { int m_blk; int n0; int width; };
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int bn) {
     TileCoord c;
-    if (t < p.full_tiles) {
-        c.m_blk = t % p.num_m_blocks;
-        c.n0 = (t / p.num_m_blocks) * bn;
-        c.width = bn;
-    } else {
+    int tt = t, half = -1;
+    if (t >= p.full_tiles) {
         const int u = t - p.full_tiles;
-        const int tt = p.full_tiles + (u >> 1);
-        c.m_blk = tt % p.num_m_blocks;
-        c.width = bn >> 1;
-        c.n0 = (tt / p.num_m_blocks) * bn + (u & 1) * c.width;
+        tt = p.full_tiles + (u >> 1);
+        half = u & 1;
     }
+    int n_blk;
+    if (p.raster_n) { n_blk = tt % p.num_n_blocks; c.m_blk = tt / p.num_n_blocks; }
+    else { c.m_blk = tt % p.num_m_blocks; n_blk = tt / p.num_m_blocks; }
+    c.width = half < 0 ? bn : bn >> 1;
+    c.n0 = n_blk * bn + (half > 0 ? c.width : 0);
     return c;
 }
 
@@ -376,7 +388,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == kWarpMma && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps * CG); }
-        if (MODE == kStTma)
+        if (is_push<MODE>())
             for (int s = 0; s < Cfg::kStoreSlots; ++s) { mbar_init(sfull_bar(s), kNumEpiWarps); mbar_init(sfree_bar(s), 1); }
         fence_mbar_init();
         fence_proxy_async_smem();
@@ -492,10 +504,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (MODE == kStTma && warp == kWarpStore) {
-        // ===================== TMA-store issuer (kStTma) =====================
+    } else if (is_push<MODE>() && warp == kWarpStore) {
+        // ===================== store issuer (kStTma / kStWide) =====================
         // Walks the same (tile, box) sequence as the epilogue warps.  Per box: wait until the four epilogue warps
-        // have filled the slot, issue one TMA store per destination, commit; then recycle the slot whose stores have
+        // have filled the slot, issue the stores to every destination, commit; then recycle the slot whose stores have
         // finished READING shared memory (the writes themselves stay in flight).
         if constexpr (MODE == kStTma) {
             const bool elected = elect_one();
@@ -526,21 +538,49 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (elected) bulk_wait_group_all();                   // all writes performed before the CTA retires
             __syncwarp();
+        } else if constexpr (MODE == kStWide) {
+            // one box per tile: 128 rows x the tile width, coordinates in 16-bit elements
+            const bool elected = elect_one();
+            const int n_dst = p.store_mc >> 8;
+            constexpr int kInflight = 1;
+            uint32_t seq = 0;
+            for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                const TileCoord tc = decode_tile(p, tile, BN);
+                const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+                if (tc.n0 >= p.N) continue;
+                const uint32_t slot = seq % Cfg::kStoreSlots;
+                mbar_wait(sfull_bar(slot), (seq / Cfg::kStoreSlots) & 1);
+                if (elected) {
+                    if (m_idx < p.M) {
+                        const uint32_t src = stage_base + slot * Cfg::kSlotBytes;
+                        for (int d = 0; d < n_dst; ++d) tma_store_2d(&smaps.m[d], src, tc.n0, m_idx);
+                    }
+                    bulk_commit_group();
+                    bulk_wait_group_read<kInflight>();
+                    if (seq >= (uint32_t)kInflight) mbar_arrive(sfree_bar((seq - kInflight) % Cfg::kStoreSlots));
+                }
+                __syncwarp();
+                ++seq;
+            }
+            if (elected) bulk_wait_group_all();
+            __syncwarp();
         }
-    } else if (MODE == kStTma) {
-        // ===================== epilogue, TMA-store flavour (warps 0..3) =====================
-        // tcgen05.ld -> scale/bias -> out dtype -> 128B-swizzled box in shared memory.  Lane = row; a 16-byte piece
-        // j of row r lives at r*128 + ((j ^ (r & 7)) * 16): conflict-free st.shared.v4 and exactly the layout the
-        // SWIZZLE_128B tensor map of the store expects.  Column/row edges need no code: TMA clips the box.
-        if constexpr (MODE == kStTma) {
+    } else if (is_push<MODE>()) {
+        // ===================== epilogue, store-ring flavour (warps 0..3) =====================
+        // tcgen05.ld -> scale/bias -> out dtype -> a box in shared memory.  Lane = row.  kStTma: 128 bytes per row,
+        // 16-byte piece j of row r at r*128 + ((j ^ (r & 7)) * 16) -- conflict-free st.shared.v4 and exactly the layout the
+        // SWIZZLE_128B tensor map of the store expects.  kStWide: BN 16-bit columns per row, linear.  Column/row edges
+        // need no code in either form: TMA clips the box.
+        if constexpr (is_push<MODE>()) {
+            constexpr bool kWide = MODE == kStWide;
             const int q = warp & 3;
             const int row_in_tile = q * 32 + lane;
             const Epi& e = p.epi;
             const float sr = e.sr ? *e.sr : 1.0f;
             const float sb0 = e.sb[0];
             const bool is_f32 = e.out_dtype == FP8B_F32;
-            const int cols_per_box = is_f32 ? 32 : 64;
-            const uint32_t row_off = (uint32_t)row_in_tile * 128u;
+            const int cols_per_box = kWide ? BN : 128 / (is_f32 ? 4 : 2);      // kStWide: one box per tile (16-bit outputs only)
+            const uint32_t row_off = (uint32_t)row_in_tile * (kWide ? (uint32_t)(BN * 2) : 128u);
             uint32_t seq = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -559,9 +599,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     __syncwarp();
                     tmem_ld_x32(t_row + c0, r);
                     const int n0 = n_idx + c0;
-                    const int n_box = n_idx + (c0 & ~(cols_per_box - 1));
-                    const bool box_first = (c0 & (cols_per_box - 1)) == 0;
-                    const bool box_last = ((c0 + 32) & (cols_per_box - 1)) == 0;
+                    const int n_box = kWide ? n_idx : n_idx + (c0 & ~(cols_per_box - 1));
+                    const bool box_first = kWide ? c0 == 0 : (c0 & (cols_per_box - 1)) == 0;
+                    const bool box_last = kWide ? false : ((c0 + 32) & (cols_per_box - 1)) == 0;    // (or the tile's last chunk, below)
                     const bool box_ok = n_box < p.N;                                   // warp-uniform
                     const bool chunk_ok = n0 < p.N;
                     float sbv[32];
@@ -599,12 +639,14 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                             if (e.sr) x = __fmul_rn(x, sr);
                             v[j] = x;
                         }
-                        const uint32_t dst = stage_base + slot * kStoreBoxBytes + row_off;
-                        const uint32_t sw = (uint32_t)(lane & 7);
+                        const uint32_t dst = stage_base + slot * Cfg::kSlotBytes + row_off;
+                        const uint32_t sw = kWide ? 0u : (uint32_t)(lane & 7);
+                        // first 16-byte piece of this chunk inside the box row
+                        const uint32_t piece0 = kWide ? (uint32_t)(c0 >> 3) : (uint32_t)(((c0 & (cols_per_box - 1)) * (is_f32 ? 4 : 2)) >> 4);
                         if (is_f32) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                sts_v4(dst + (((uint32_t)j ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                sts_v4(dst + (((piece0 + j) ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                        __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
                         } else {
                             uint32_t pk[16];
@@ -618,7 +660,6 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                     pk[j] = *reinterpret_cast<uint32_t*>(&h);
                                 }
                             }
-                            const uint32_t piece0 = (uint32_t)((c0 & 32) >> 3);        // 0 or 4: which half of the 128-byte row
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 sts_v4(dst + (((piece0 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
@@ -835,21 +876,22 @@ static PFN_encodeTiled get_encode_fn()
 // analogue of the reference bridge's one-time pipeline cache, fp8_bridge.cpp:103-141).  A map holds only addresses
 // and extents, never data, so a stale entry for a freed-and-reallocated pointer with the same geometry is still right.
 struct MapKey {
-    const void* base; uint64_t rows, row_bytes, pitch; uint32_t box_rows, box_bytes;
+    const void* base; uint64_t rows, row_bytes, pitch; uint32_t box_rows, box_bytes, esz_swz;
     bool operator==(const MapKey& o) const {
         return base == o.base && rows == o.rows && row_bytes == o.row_bytes && pitch == o.pitch &&
-               box_rows == o.box_rows && box_bytes == o.box_bytes;
+               box_rows == o.box_rows && box_bytes == o.box_bytes && esz_swz == o.esz_swz;
     }
 };
 struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
 constexpr int kMapCacheSlots = 64;
 
-// rows x row_bytes uint8 matrix with a row pitch, box = box_rows x box_bytes (<= 128), 128B swizzle.
+// rows x row_elems matrix of esz-byte elements with a row pitch (bytes), box = box_rows x box_elems; 128B swizzle
+// (box_elems * esz <= 128) or none (linear box, box_elems <= 256).
 static bool get_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, uint64_t row_bytes, uint64_t pitch,
-                           uint32_t box_rows, uint32_t box_bytes)
+                           uint32_t box_rows, uint32_t box_bytes, uint32_t esz = 1, bool swizzle128 = true)
 {
     static thread_local MapSlot cache[kMapCacheSlots];
-    const MapKey key = {base, rows, row_bytes, pitch, box_rows, box_bytes};
+    const MapKey key = {base, rows, row_bytes, pitch, box_rows, box_bytes, esz * 2 + (swizzle128 ? 1u : 0u)};
     uint64_t h = reinterpret_cast<uintptr_t>(base) >> 4;
     h ^= rows * 0x9E3779B97F4A7C15ull; h ^= row_bytes * 0xC2B2AE3D27D4EB4Full; h ^= pitch << 7; h ^= (uint64_t)box_rows << 40;
     h ^= h >> 29;
@@ -861,8 +903,9 @@ static bool get_tensor_map(CUtensorMap* out, const void* base, uint64_t rows, ui
     cuuint64_t strides[1] = {(cuuint64_t)pitch};
     cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(out, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     s.key = key; s.map = *out; s.valid = true;
@@ -881,11 +924,14 @@ bool tcgen05_supported(const MMArgs& a)
     return a.M >= 1 && a.N >= 1 && a.K >= 16 && (a.K % 16 == 0) && aligned(a.A, 16) && aligned(a.B, 16);
 }
 
-// TMA-store epilogue: every destination base and the row pitch must be 16-byte aligned
+// TMA-store epilogue: every destination base, the row pitch and the row length must be multiples of 16 bytes
 static bool tma_store_ok(const MMArgs& a, void* const* dsts, int n_dst)
 {
     const size_t esz = dtype_size(a.out_dtype);
     if ((a.ldc * esz) % 16 != 0) return false;
+    // TMA stores move 16-byte units: a row of the column block that does not end on one would be rounded UP and the
+    // store would write past column N (seen: three columns of a neighbour's shard zeroed)
+    if (((size_t)a.N * esz) % 16 != 0) return false;
     for (int d = 0; d < n_dst; ++d)
         if (!dsts[d] || !aligned(dsts[d], 16)) return false;
     return true;
@@ -908,6 +954,14 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.num_m_blocks = (a.M + kBM * CG - 1) / (kBM * CG);
     p.num_n_blocks = (a.N + BN - 1) / BN;
     p.num_k_blocks = (a.K + kBK - 1) / kBK;
+    {   // Tile order.  N fastest: the tiles in flight complete whole output rows together (DRAM-page- and NVLink-friendly
+        // writes; the C4 shard at w = 2: 53.2 vs 58.6 us) and re-read B once per 256-row block from L2 -- fine while B
+        // stays L2-resident.  Otherwise the smaller operand is the one to re-read.
+        const int forced_r = tune(kTuneGemmRaster, 0);
+        const size_t b_bytes = (size_t)a.N * a.K, a_bytes = (size_t)a.M * a.K;
+        const bool n_fast = b_bytes <= ((size_t)48 << 20) || b_bytes <= a_bytes;
+        p.raster_n = forced_r ? (forced_r == 2) : n_fast;
+    }
     const int tiles_all = p.num_m_blocks * p.num_n_blocks;
     const int workers_cap = device_info().sm_count / CG;
     p.full_tiles = tiles_all;
@@ -916,6 +970,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
         const int rem = tiles_all % workers_cap;
         bool can_split = (BN % 64 == 0) && ((BN / 2 / CG) % 8 == 0) && tiles_all > workers_cap;
         if (MODE == kStTma) can_split = can_split && ((BN / 2) * esz) % 128 == 0;      // half tiles must be whole store boxes
+        if (MODE == kStWide) can_split = false;                                        // one fixed-width box per tile
 #ifdef FP8B_PROFILE
         can_split = can_split && !(tune_int("FP8B_GEMM_DEBUG", 0) & 8);
 #endif
@@ -943,6 +998,16 @@ static int launch_tcgen05_cfg(const MMArgs& a)
             if (!get_tensor_map(&smaps.m[d], dsts[d], (uint64_t)a.M, (uint64_t)a.N * esz, (uint64_t)a.ldc * esz, 128, 128))
                 return FP8B_ERR_CUDA;
         for (int d = n_dst; d < kMaxDst; ++d) smaps.m[d] = smaps.m[0];
+    } else if constexpr (MODE == kStWide) {  // same arguments; 16-bit outputs, one linear box per tile
+        const int n_dst = a.store_mc >> 8;
+        void* const* dsts = static_cast<void* const*>(a.ws);
+        void* self[1] = {a.C};
+        if (!dsts) dsts = self;
+        if (esz != 2 || n_dst < 1 || n_dst > kMaxDst || !tma_store_ok(a, dsts, n_dst)) return FP8B_ERR_UNSUPPORTED;
+        for (int d = 0; d < n_dst; ++d)
+            if (!get_tensor_map(&smaps.m[d], dsts[d], (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ldc * 2, 128, BN, 2, false))
+                return FP8B_ERR_CUDA;
+        for (int d = n_dst; d < kMaxDst; ++d) smaps.m[d] = smaps.m[0];
     } else {
         smaps.unused = 0;
 #ifdef FP8B_PROFILE
@@ -956,7 +1021,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
 #endif
     }
     // multimem.st / peer stores have no sub-word form: both modes need every chunk on the 16-byte path
-    if (MODE != kStTma && a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
+    if (!is_push<MODE>() && a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
     const int tiles = p.num_work;
     const int workers_max = workers_cap;                            // one CTA (or CTA pair) per SM (pair)
@@ -995,7 +1060,9 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     return after_launch();
 }
 
-constexpr int kDefaultGemmStore = 1;      // epilogue of plain fp8b_scaled_mm calls: 1 = st.global, 2 = TMA store (measured choice)
+constexpr bool kPushWideDefault = false;   // push to peers: one linear box per tile instead of 128-byte-wide boxes (measured choice)
+constexpr int kDefaultGemmStore = 2;      // epilogue of plain fp8b_scaled_mm calls: 1 = st.global from the epilogue warps, 2 = TMA
+                                          // store (C4: 109.7 vs 112.0 us in the same bench run; falls back to 1 when C is not TMA-storable)
 
 // Tile configuration: 1 = 128x256 one CTA, 2 = 128x128 one CTA, 3 = 256x256 pair, 4 = 256x128 pair, 5 = 256x192 pair.
 static int pick_tile_cfg(const MMArgs& a)
@@ -1031,8 +1098,12 @@ int launch_gemm_tcgen05(const MMArgs& a)
     // 256-wide when that still leaves >= ~2 waves of tiles, else 128-wide (finer tail).
     // fp8b_set_option(FP8B_OPT_TUNE_GEMM_CFG) -- a result-neutral tuning knob -- forces one.
     const int forced = tune(kTuneGemmCfg, 0);
-    const int cfg = forced ? forced : pick_tile_cfg(a);
+    int cfg = forced ? forced : pick_tile_cfg(a);
     const int mode = a.store_mc & 0xFF;
+    // Pushing to peers the kernel is bound by NVLink, not by the tensor pipe, and the link idles until the first tiles
+    // are complete: narrower tiles (256 x 128) halve that ramp at no cost in exchange time (measured at w = 2:
+    // 103.4 us against 106.4 us with 256 x 256 tiles; profiles/r2_scaling.md).
+    if (!forced && mode == 3 && (a.store_mc >> 8) > 1 && (cfg == 3 || cfg == 5)) cfg = 4;
     if (mode == 2) {          // peer stores with st.global (round-1 plan): the CTA-pair configurations only
         if ((a.store_mc >> 8) < 2 || (a.store_mc >> 8) > 8 || !a.ws) return FP8B_ERR_INVALID;
         switch (cfg) {
@@ -1042,7 +1113,20 @@ int launch_gemm_tcgen05(const MMArgs& a)
             default: return FP8B_ERR_UNSUPPORTED;
         }
     }
-    if (mode == 3) {          // TMA-store epilogue, 1..8 destinations
+    if (mode == 3) {          // store-ring epilogue, 1..8 destinations
+        // 16-bit outputs going to peers: one linear box per tile (256- / 512-byte NVLink writes); else 128-byte-wide
+        // swizzled boxes.  FP8B_OPT_TUNE_GEMM_STORE 3 / 4 force the wide / the 128-byte form.
+        const int st = tune(kTuneGemmStore, 0);
+        const bool wide = dtype_size(a.out_dtype) == 2 && (st == 3 || (st != 4 && kPushWideDefault && (a.store_mc >> 8) > 1));
+        if (wide) {
+            switch (cfg) {
+                case 1: return launch_tcgen05_cfg<256, 1, kStWide>(a);
+                case 3: return launch_tcgen05_cfg<256, 2, kStWide>(a);
+                case 4: return launch_tcgen05_cfg<128, 2, kStWide>(a);
+                case 5: return launch_tcgen05_cfg<192, 2, kStWide>(a);
+                default: return launch_tcgen05_cfg<128, 1, kStWide>(a);
+            }
+        }
         switch (cfg) {
             case 1: return launch_tcgen05_cfg<256, 1, kStTma>(a);
             case 3: return launch_tcgen05_cfg<256, 2, kStTma>(a);

@@ -502,15 +502,18 @@ int launch_gemv(const MMArgs& a)
     // kernel choice: M == 1 -> CUDA-core FHFMA kernel (exact fp32 accumulation order per lane);
     // M >= 2 -> warp-level tensor-core kernel (weights streamed once for all M rows).
     // FP8B_GEMV_IMPL=1 / 2 forces the first / second (profiling knob).
-    const int impl = tune(kTuneGemvImpl, 0);
+    int impl = tune(kTuneGemvImpl, 0);
     if (a.a_fmt | a.b_fmt) {        // an e5m2 operand: the warp-MMA kernel has all four type pairs; else the generic kernel
         if (gemv_mma_supported(a)) return launch_gemv_mma(a);
         fp8_gemv_generic_kernel<<<(a.N + kGemvWarps - 1) / kGemvWarps, kGemvThreads, 0, a.st>>>(a.A, a.B, a.M, a.N, a.K, make_epi(a),
                                                                                              a.a_fmt, a.b_fmt);
         return after_launch();
     }
-    // impl 4 (and the default where it applies): the persistent TMA-ring kernel, one design for M = 1..16
-    if ((impl == 4 || (impl == 0 && kGemvRingDefault)) && !a.chain_pdl && gemv_ring_supported(a)) return launch_gemv_ring(a);
+    // impl 4: the persistent TMA-ring kernel (fp8_gemv_ring.cu); where it does not apply the default rule decides
+    if (impl == 4 || (impl == 0 && kGemvRingDefault)) {
+        if (!a.chain_pdl && gemv_ring_supported(a)) return launch_gemv_ring(a);
+        impl = 0;
+    }
     if (gemv_mma_supported(a) && (impl == 2 || (impl == 0 && a.M >= 2))) return launch_gemv_mma(a);
     if (gemv_rows_supported(a) && (impl == 3)) return launch_gemv_rows(a);
     const Epi epi = make_epi(a);

@@ -96,6 +96,7 @@ def _same_accel_device(tensor, device):
 # --------------------------------------------------------------------------- _scaled_mm
 
 _SCALED_MM_POSITIONAL = ("scale_a", "scale_b", "bias", "scale_result", "out_dtype", "use_fast_accum")
+_FP8_DTYPES = frozenset(d for d in (_E4M3, _E5M2) if d is not None)
 _FP8_LIKE = frozenset(d for d in (torch.uint8, _E4M3, _E5M2) if d is not None)     # fp8_mps_patch.py:64-65
 _scaled_mm_patch_fn = None
 
@@ -177,6 +178,16 @@ def _metal_tensor_to(self, *args, **kwargs):
     3. FP8 tensor on the GPU: no-op, FP8<->FP8 reinterpretation, or exact dequantise.
     Everything else goes to the original method untouched.
     """
+    # Fast exit for the overwhelmingly common call that involves no FP8 at all: this wrapper sits on EVERY Tensor.to()
+    # in the process (a10 in SURVEY 8a), so the non-FP8 path must cost next to nothing.
+    if self.dtype not in _FP8_DTYPES and kwargs.get("dtype") is not _E4M3:
+        for a in args:
+            if a is _E4M3:
+                break
+            if isinstance(a, torch.Tensor) and a.dtype is _E4M3:
+                break
+        else:
+            return _original_tensor_to(self, *args, **kwargs)
     dtype, device = _parse_to_args(args, kwargs)
     src_fp8 = _is_fp8_dtype(self.dtype)
     dst_fp8 = _is_fp8_dtype(dtype)
@@ -227,12 +238,10 @@ def _metal_tensor_copy(self, src, non_blocking=False):
     with torch's own cast (the reference would store e4m3fn codes in it).  Everything else goes
     to the original method.
     """
-    if not hasattr(src, "dtype"):
+    # fast exit: only FP8 destinations on the accelerator are intercepted (this wrapper sits on every copy_())
+    if self.dtype not in _FP8_DTYPES or not self.is_cuda or not hasattr(src, "dtype"):
         return _original_tensor_copy(self, src, non_blocking=non_blocking)
     src_fp8 = _is_fp8_dtype(src.dtype)
-    dst_fp8 = _is_fp8_dtype(self.dtype)
-    if self.device.type != ACCEL or not dst_fp8:
-        return _original_tensor_copy(self, src, non_blocking=non_blocking)
 
     if src_fp8:
         _original_tensor_copy(self.view(torch.uint8), src.contiguous().view(torch.uint8), non_blocking=non_blocking)

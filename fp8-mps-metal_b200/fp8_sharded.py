@@ -232,8 +232,12 @@ class ShardedScaledMM:
         if dist.get_backend(self.group) != "nccl":
             return False
         esz = torch.empty((), dtype=odt).element_size()
-        if K < 16 or K % 16 or (self.N * esz) % 16 or (self.width * esz) % 16:
+        if K < 16 or K % 16 or (self.N * esz) % 16:
             return False
+        for r in range(self.world):                              # every rank's column block: start and length in 16-byte units
+            n0, n1, _ = shard_bounds(self.N, self.world, r, self.align)
+            if (n0 * esz) % 16 or ((n1 - n0) * esz) % 16:
+                return False
         return True
 
     def forward_push(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:

@@ -93,6 +93,7 @@ FP8B_API uint64_t fp8b_launch_count(void);
  *                              CAST_SHAPE    cast launch shape: 1 = small tiles, 2 = big tiles
  *                              GEMM_STORE    tcgen05 epilogue: 1 = st.global from the epilogue warps, 2 = TMA store
  *                              GEMV_UNROLL / GEMV_BATCH / AMAX_CAP   load batching of the GEMV kernels / amax grid cap
+ *                              GEMM_RASTER   tcgen05 tile order: 1 = M fastest, 2 = N fastest (whole output rows complete together)
  */
 typedef enum fp8b_option {
     FP8B_OPT_PDL = 0,
@@ -104,7 +105,8 @@ typedef enum fp8b_option {
     FP8B_OPT_TUNE_GEMM_STORE = 20,
     FP8B_OPT_TUNE_GEMV_UNROLL = 21,
     FP8B_OPT_TUNE_GEMV_BATCH = 22,
-    FP8B_OPT_TUNE_AMAX_CAP = 23
+    FP8B_OPT_TUNE_AMAX_CAP = 23,
+    FP8B_OPT_TUNE_GEMM_RASTER = 24
 } fp8b_option;
 FP8B_API int fp8b_set_option(int option, int value);
 FP8B_API int fp8b_get_option(int option);
@@ -331,8 +333,9 @@ FP8B_API int fp8b_scaled_mm_peers(const uint8_t* A, const uint8_t* B, void* C_lo
  * The epilogue warps only fill a shared-memory ring; a dedicated warp issues cp.async.bulk.tensor stores, several
  * in flight, so the tensor-memory accumulator is released as soon as it is drained and NVLink writes overlap the
  * next tile's MMAs.  Each GPU receives (world-1)/world of the output.  The caller orders ranks around the call (a
- * barrier before a buffer is reused and one after).  Needs 16-byte aligned A / B / every C_dsts[d], K % 16 == 0 and
- * ldc * sizeof(out) % 16 == 0 (fp8b_scaled_mm_push_supported); any M, N (TMA clips the edges).  Else FP8B_ERR_UNSUPPORTED.
+ * barrier before a buffer is reused and one after).  Needs 16-byte aligned A / B / every C_dsts[d], K % 16 == 0,
+ * ldc * sizeof(out) % 16 == 0 and N * sizeof(out) % 16 == 0 (TMA stores move 16-byte units); otherwise any M, N -- TMA
+ * clips the tile edges (fp8b_scaled_mm_push_supported).  Else FP8B_ERR_UNSUPPORTED.
  */
 FP8B_API int fp8b_scaled_mm_push(const uint8_t* A, const uint8_t* B, void* const* C_dsts, int n_dst,
                         int out_dtype, int M, int N, int K, int64_t ldc,

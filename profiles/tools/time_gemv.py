@@ -27,9 +27,10 @@ for name, M, K, N, odt, nbytes, rot in CFG:
                                   None, None, 0, 1, st)
             assert rc == 0, rc
     res = []
-    for impl in (0, 1, 2, 4):
+    for impl in (0, 1, 2, 4, 42):
         for static in (0, 1):
-            L.fp8b_set_option(17, impl if impl else -1); L.fp8b_set_option(1, static)
+            L.fp8b_set_option(17, (impl if impl < 10 else 4) if impl else -1); L.fp8b_set_option(1, static)
+            L.fp8b_set_option(21, 2 if impl == 42 else -1)              # ring kernel: two half-size rings per SM
             try:
                 for _ in range(2): run()
                 torch.cuda.synchronize()
@@ -48,7 +49,7 @@ for name, M, K, N, odt, nbytes, rot in CFG:
                 res.append(f"impl{impl}{'s' if static else ' '} {best:6.2f} us {nbytes / best / 1e3:5.0f} GB/s")
             except Exception as e:
                 res.append(f"impl{impl}{'s' if static else ' '} ERR {str(e)[:40]}")
-    L.fp8b_set_option(17, -1); L.fp8b_set_option(1, 0)
+    L.fp8b_set_option(17, -1); L.fp8b_set_option(1, 0); L.fp8b_set_option(21, -1)
     print(f"{name:3s} M{M} K{K} N{N}: " + " | ".join(res), flush=True)
     del Ws
     torch.cuda.empty_cache()

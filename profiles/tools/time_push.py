@@ -59,12 +59,16 @@ def timeit(fn, name):
     print(f"{name:28s} M{M} K{K} N{N}: {best:8.2f} us  {2.0*M*N*K/best/1e6:7.0f} TFLOP/s", flush=True)
 
 
-for cfg in ([0, 3, 5, 4] if len(sys.argv) <= 4 else [0]):
-    L.fp8b_set_option(16, cfg if cfg else -1)
-    timeit(direct, f"cfg{cfg} st.global epilogue")
-    timeit(push(1), f"cfg{cfg} TMA store x1")
-    timeit(push(2), f"cfg{cfg} TMA store x2 (local)")
-L.fp8b_set_option(16, -1)
+for raster in (1, 2):
+    L.fp8b_set_option(24, raster)
+    for cfg in ([0, 3, 5, 4] if len(sys.argv) <= 4 else [0]):
+        L.fp8b_set_option(16, cfg if cfg else -1)
+        L.fp8b_set_option(20, 1)
+        timeit(direct, f"raster{raster} cfg{cfg} st.global epilogue")
+        L.fp8b_set_option(20, -1)
+        timeit(push(1), f"raster{raster} cfg{cfg} TMA store x1")
+        timeit(push(2), f"raster{raster} cfg{cfg} TMA store x2 (local)")
+L.fp8b_set_option(16, -1); L.fp8b_set_option(24, -1)
 torch.cuda.synchronize()
 sets[0][2].zero_(); sets[0][3].zero_()
 direct(); ref = sets[0][2].clone(); sets[0][2].zero_()

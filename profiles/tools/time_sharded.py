@@ -22,6 +22,62 @@ variants = {"compute_only": lambda: lin.local(a, sa, torch.bfloat16),
             "multicast_fused": lambda: lin(a, sa, torch.bfloat16, mode="multicast"),
             "peer_store_fused": lambda: lin(a, sa, torch.bfloat16, mode="peers"),
             "push_fused": lambda: lin(a, sa, torch.bfloat16, mode="push")}
+def push_kernel_only():
+    # the fused kernel alone, without the closing symmetric-memory barrier (timing breakdown only)
+    key, pair, turn = lin._symm_buffers(M, torch.bfloat16, dev)
+    buf, hdl = pair[turn]
+    nat._get_lib().fp8_scaled_mm_push(a, lin.weight, sa, lin.scale_b, None, buf, lin._push_order(turn, hdl), int(lin.n0))
+def barrier_only():
+    key, pair, turn = lin._symm_buffers(M, torch.bfloat16, dev)
+    pair[turn][1].barrier(channel=0)
+variants["push_kernel_only"] = push_kernel_only
+variants["barrier_only"] = barrier_only
+for cfg in [int(c) for c in os.environ.get("CFGS", "").split(",") if c]:
+    def mk(cfg):
+        def run():
+            nat._get_lib().set_option(16, cfg)
+            try:
+                lin(a, sa, torch.bfloat16, mode="push")
+            finally:
+                nat._get_lib().set_option(16, -1)
+        return run
+    variants[f"push_cfg{cfg}"] = mk(cfg)
+for st_name, st_val in (("push_box128", 4), ("push_wide", 3)):
+    def mk2(v):
+        def run():
+            nat._get_lib().set_option(20, v)
+            try:
+                lin(a, sa, torch.bfloat16, mode="push")
+            finally:
+                nat._get_lib().set_option(20, -1)
+        return run
+    variants[st_name] = mk2(st_val)
+    def mk3(v):
+        def run():
+            nat._get_lib().set_option(20, v)
+            try:
+                push_kernel_only()
+            finally:
+                nat._get_lib().set_option(20, -1)
+        return run
+    variants[st_name + "_kernel_only"] = mk3(st_val)
+def mk_raster(v, kernel_only):
+    def run():
+        nat._get_lib().set_option(24, v)
+        try:
+            push_kernel_only() if kernel_only else lin(a, sa, torch.bfloat16, mode="push")
+        finally:
+            nat._get_lib().set_option(24, -1)
+    return run
+variants["push_rasterN"] = mk_raster(2, False)
+variants["push_rasterN_kernel_only"] = mk_raster(2, True)
+def compute_rasterN():
+    nat._get_lib().set_option(24, 2)
+    try:
+        lin.local(a, sa, torch.bfloat16)
+    finally:
+        nat._get_lib().set_option(24, -1)
+variants["compute_only_rasterN"] = compute_rasterN
 only = os.environ.get("ONLY")
 if only:
     variants = {k: v for k, v in variants.items() if k in only.split(",")}
@@ -41,10 +97,14 @@ for name, fn in variants.items():
         out[name] = repr(e)[:120]
 # parity of the push plan against the all-gather of the same shards
 try:
+    nat._get_lib().set_option(20, 3)
+    y_wide = lin(a, sa, torch.bfloat16, mode="push").clone()
+    nat._get_lib().set_option(20, -1)
     y_push = lin(a, sa, torch.bfloat16, mode="push").clone()
     y_ag = lin(a, sa, torch.bfloat16, layout="row_major")
     torch.cuda.synchronize()
     out["push==allgather"] = bool(torch.equal(y_push, y_ag))
+    out["push_wide==allgather"] = bool(torch.equal(y_wide, y_ag))
 except Exception as e:
     out["push==allgather"] = repr(e)[:200]
 if rank == 0:

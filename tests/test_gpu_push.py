@@ -66,14 +66,20 @@ def _case(M, K, N, odt, n_dst=1, ldc=None, n0=0, per_row=False, bias_dt=None, sc
     (128, 128, 8, torch.bfloat16, dict(n_dst=2, ldc=24, n0=8)),                 # one partial box
     (2048, 768, 4096 + 64, torch.bfloat16, dict(n_dst=2)),                      # last-wave split + ragged last tile
 ])
-def test_push_matches_direct_and_oracle(M, K, N, odt, kw):
+@pytest.mark.parametrize("store", [4, 3])
+def test_push_matches_direct_and_oracle(tune, store, M, K, N, odt, kw):
+    """store = 4: 128B-swizzled boxes of 128-byte rows; store = 3: one linear box per tile, 256- / 512-byte rows
+    (16-bit outputs; fp32 keeps the 128-byte form) -- FP8B_OPT_TUNE_GEMM_STORE."""
+    tune("GEMM_STORE", store)
     _case(M, K, N, odt, seed=M + K + N, **kw)
 
 
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
-def test_push_all_tile_configs(tune, cfg):
-    """Every tile configuration (FP8B_OPT_TUNE_GEMM_CFG) with the TMA-store epilogue."""
+@pytest.mark.parametrize("store", [4, 3])
+def test_push_all_tile_configs(tune, cfg, store):
+    """Every tile configuration (FP8B_OPT_TUNE_GEMM_CFG) with both store-ring epilogues."""
     tune("GEMM_CFG", cfg)
+    tune("GEMM_STORE", store)
     _case(640, 512, 1000, torch.bfloat16, n_dst=2, ldc=2000, n0=1000, per_row=True, bias_dt=torch.bfloat16, seed=11)
     _case(300, 256, 328, torch.float32, n_dst=1, seed=12)
     _case(1280, 384, 2560, torch.float16, n_dst=2, seed=13)
@@ -119,4 +125,50 @@ def test_push_rejects_unaligned():
     dst = torch.zeros(M, 37, dtype=torch.bfloat16, device=DEV)              # row pitch 74 bytes: not TMA-storable
     assert mm_push_capi(tA, tB, one, one, [dst[:, :N]]) == -2               # FP8B_ERR_UNSUPPORTED, never a fallback
     assert L.fp8b_scaled_mm_push_supported(2, M, N, K, 37, None, None, None) == 0
-    assert L.fp8b_scaled_mm_push_supported(2, M, N, K, 40, None, None, None) == 1
+    assert L.fp8b_scaled_mm_push_supported(2, M, N, K, 40, None, None, None) == 0      # 36 columns = 72 bytes: not 16-byte units
+    assert L.fp8b_scaled_mm_push_supported(2, M, 32, K, 40, None, None, None) == 1
+
+
+@pytest.mark.parametrize("store", [4, 3])
+def test_push_ragged_column_block(tune, store):
+    """A column block whose rows end on a 16-byte boundary but not on a box boundary: the tensor map clips the last box
+    in both store forms.  A block that does not end on 16 bytes is refused (TMA stores move 16-byte units and would
+    write past column N) -- and plain fp8b_scaled_mm, whose default epilogue is the TMA store, falls back to st.global."""
+    tune("GEMM_STORE", store)
+    _case(300, 256, 328, torch.bfloat16, n_dst=2, ldc=1000, n0=8, per_row=True, seed=3)
+    M, K, N = 130, 64, 333
+    tA = torch.from_numpy(_bytes((M, K), 1)).to(DEV)
+    tB = torch.from_numpy(_bytes((N, K), 2)).to(DEV)
+    one = torch.ones(1, device=DEV)
+    dst = torch.full((M, 1000), -7.0, dtype=torch.bfloat16, device=DEV)
+    assert mm_push_capi(tA, tB, one, one, [dst], n0=8) == -2
+    assert capi().fp8b_scaled_mm_push_supported(2, M, N, K, 1000, None, None, None) == 0
+    tune("GEMM_STORE", 2)
+    rc, c = mm_capi(tA, tB, one, one, None, None, torch.bfloat16, ALGO_TCGEN05, out=dst[:, 8:8 + N])
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert bool((dst[:, :8] == -7.0).all()) and bool((dst[:, 8 + N:] == -7.0).all())
+    ref = o.scaled_mm(_bytes((M, K), 1), _bytes((N, K), 2), np.ones(1, np.float32), np.ones(1, np.float32), None, None, "bf16")
+    assert o.rel_rmse(to_np(dst[:, 8:8 + N]), ref) <= 3e-3
+
+
+@pytest.mark.parametrize("M,K,N,odt", [(2304, 256, 2560, torch.bfloat16), (1000, 512, 3000, torch.float16), (300, 128, 520, torch.float32)])
+def test_tile_raster_orders_agree(tune, M, K, N, odt):
+    """FP8B_OPT_TUNE_GEMM_RASTER: M-fastest and N-fastest tile orders (incl. the split last wave) give the same bits, with
+    both epilogues."""
+    A, B = _bytes((M, K), 21), _bytes((N, K), 22)
+    tA, tB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+    s = torch.full((1,), 0.01, device=DEV)
+    outs = []
+    for raster in (1, 2):
+        for store in (1, 2):
+            tune("GEMM_RASTER", raster)
+            tune("GEMM_STORE", store)
+            rc, c = mm_capi(tA, tB, s, s, None, None, odt, ALGO_TCGEN05)
+            assert rc == 0
+            outs.append(c)
+    torch.cuda.synchronize()
+    for c in outs[1:]:
+        assert torch.equal(outs[0], c)
+    ref = o.scaled_mm(A, B, np.full(1, 0.01, np.float32), np.full(1, 0.01, np.float32), None, None, dt_name(odt))
+    assert o.rel_rmse(to_np(outs[0]), ref) <= TOL[dt_name(odt)]

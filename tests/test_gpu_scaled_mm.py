@@ -163,7 +163,7 @@ def test_gemv_mma_nan_bytes(tune):
     (2, 4160, 1184, None, {"per_row_a": True, "per_row_b": True}),     # minimum N (8 rows per SM), K = 65 chunks
     (8, 2048, 5001, torch.float16, {"per_row_a": True, "bias_dtype": torch.float32, "scale_result": True}),  # ragged N
     (9, 1024, 3000, None, {"per_row_a": True}),                # two activation tiles (M > 8)
-    (16, 4096, 2400, torch.bfloat16, {"per_row_b": True, "bias_dtype": torch.bfloat16}),   # largest x: 66 KB of shared memory
+    (16, 2048, 2400, torch.bfloat16, {"per_row_b": True, "bias_dtype": torch.bfloat16}),   # largest x: 64 KB of fp16 in shared memory
     (3, 64, 1500, None, {}),                                   # one 64-byte chunk
     (1, 28672, 2000, None, {}),                                # 14 K-segments per row tile
     (5, 6208, 4096, None, {"scale_result": True}),             # K = 97 chunks: uneven last segment
