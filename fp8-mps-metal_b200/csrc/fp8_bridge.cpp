@@ -463,7 +463,9 @@ void fp8_scaled_mm_peers(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a
 // process (torch symmetric memory `buffer_ptrs`; this rank's own buffer among them), in the order they should be
 // written.  The column block [n0, n0 + N) of every destination is written.
 void fp8_scaled_mm_push(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a, torch::Tensor scale_b,
-                        c10::optional<torch::Tensor> bias, torch::Tensor out, std::vector<int64_t> dst_ptrs, int64_t n0)
+                        c10::optional<torch::Tensor> bias, torch::Tensor out, std::vector<int64_t> dst_ptrs, int64_t n0,
+                        std::vector<int64_t> signal_ptrs, c10::optional<torch::Tensor> cta_counter, int64_t epoch,
+                        c10::optional<torch::Tensor> wait_flags, int64_t rank)
 {
     TORCH_CHECK(A.dtype() == torch::kUInt8 && B.dtype() == torch::kUInt8, "A and B must be uint8 (FP8 encoded)");
     TORCH_CHECK(A.is_cuda() && B.is_cuda() && A.is_contiguous() && B.is_contiguous(), "A, B must be contiguous CUDA tensors");
@@ -490,10 +492,27 @@ void fp8_scaled_mm_push(torch::Tensor A, torch::Tensor B, torch::Tensor scale_a,
     void* dsts[8];
     for (size_t d = 0; d < dst_ptrs.size(); ++d)
         dsts[d] = reinterpret_cast<uint8_t*>(static_cast<uintptr_t>(dst_ptrs[d])) + n0 * out.element_size();
-    int rc = fp8b_scaled_mm_push(u8_ptr(A), u8_ptr(B), dsts, (int)dst_ptrs.size(), to_fp8b_dtype(out.scalar_type()),
-                                 (int)M, (int)N, (int)K, full_N, sa, (int)sa_len, sb, (int)sb_len, bias_ptr, bias_dt, nullptr,
-                                 current_stream());
-    check_status(rc, "fp8b_scaled_mm_push");
+    const int n_dst = (int)dst_ptrs.size();
+    const int odt = to_fp8b_dtype(out.scalar_type());
+    if (signal_ptrs.empty()) {
+        check_status(fp8b_scaled_mm_push(u8_ptr(A), u8_ptr(B), dsts, n_dst, odt, (int)M, (int)N, (int)K, full_N, sa, (int)sa_len,
+                                         sb, (int)sb_len, bias_ptr, bias_dt, nullptr, current_stream()),
+                     "fp8b_scaled_mm_push");
+        return;
+    }
+    // fused closing barrier: the kernel signals every peer when its last box has landed; fp8b_peer_wait (PDL) follows
+    TORCH_CHECK(signal_ptrs.size() == dst_ptrs.size(), "one signal pointer per destination (0 for this rank)");
+    TORCH_CHECK(cta_counter.has_value() && cta_counter->is_cuda() && cta_counter->scalar_type() == at::kInt, "cta_counter: CUDA int32[1]");
+    TORCH_CHECK(wait_flags.has_value() && wait_flags->is_cuda() && wait_flags->scalar_type() == at::kLong, "wait_flags: CUDA int64");
+    uint64_t* sig[8];
+    for (int d = 0; d < n_dst; ++d) sig[d] = reinterpret_cast<uint64_t*>(static_cast<uintptr_t>(signal_ptrs[d]));
+    check_status(fp8b_scaled_mm_push_signal(u8_ptr(A), u8_ptr(B), dsts, n_dst, odt, (int)M, (int)N, (int)K, full_N, sa, (int)sa_len,
+                                            sb, (int)sb_len, bias_ptr, bias_dt, nullptr, sig,
+                                            reinterpret_cast<uint32_t*>(cta_counter->data_ptr()), (uint64_t)epoch, current_stream()),
+                 "fp8b_scaled_mm_push_signal");
+    check_status(fp8b_peer_wait(reinterpret_cast<const uint64_t*>(wait_flags->data_ptr()), n_dst, (int)rank, (uint64_t)epoch,
+                                current_stream()),
+                 "fp8b_peer_wait");
 }
 
 // per-row fp8_quantize of a 2-D tensor: returns (uint8 (rows, cols), inv_scale float32 [rows])
@@ -608,7 +627,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
     m.def("fp8_scaled_mm_push", &fp8_scaled_mm_push,
           "N-sharded linear: tcgen05 GEMM whose TMA-store epilogue pushes each tile into every destination buffer",
           py::arg("A"), py::arg("B"), py::arg("scale_a"), py::arg("scale_b"), py::arg("bias"), py::arg("out"),
-          py::arg("dst_ptrs"), py::arg("n0"));
+          py::arg("dst_ptrs"), py::arg("n0"), py::arg("signal_ptrs") = std::vector<int64_t>(), py::arg("cta_counter") = py::none(),
+          py::arg("epoch") = 0, py::arg("wait_flags") = py::none(), py::arg("rank") = 0);
     m.def("push_supported", [](int64_t M, int64_t N, int64_t K, int64_t ldc, at::ScalarType dt) {
         // alignment of torch allocations (>= 256 B) is assumed; this answers the shape part
         return fp8b_scaled_mm_push_supported(to_fp8b_dtype(dt), (int)M, (int)N, (int)K, ldc, nullptr, nullptr, nullptr) != 0;

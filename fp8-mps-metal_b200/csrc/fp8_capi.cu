@@ -311,6 +311,42 @@ extern "C" int fp8b_scaled_mm_push(const uint8_t* A, const uint8_t* B, void* con
     return launch_gemm_tcgen05(a);
 }
 
+extern "C" int fp8b_scaled_mm_push_signal(const uint8_t* A, const uint8_t* B, void* const* C_dsts, int n_dst,
+                                          int out_dtype, int M, int N, int K, int64_t ldc,
+                                          const float* scale_a, int scale_a_len,
+                                          const float* scale_b, int scale_b_len,
+                                          const void* bias, int bias_dtype, const float* scale_result,
+                                          uint64_t* const* signal_flags, uint32_t* cta_counter, uint64_t epoch, void* stream)
+{
+    if (n_dst < 1 || n_dst > 8 || !C_dsts || !signal_flags || !cta_counter) return FP8B_ERR_INVALID;
+    for (int d = 0; d < n_dst; ++d)
+        if (!C_dsts[d]) return FP8B_ERR_INVALID;
+    PushSignal sig;
+    for (int d = 0; d < 8; ++d) sig.flags[d] = d < n_dst ? signal_flags[d] : nullptr;
+    sig.cta_counter = cta_counter;
+    sig.epoch = epoch;
+    MMArgs a;
+    a.A = A; a.B = B; a.C = C_dsts[0]; a.out_dtype = out_dtype; a.M = M; a.N = N; a.K = K; a.ldc = ldc;
+    a.sa = scale_a; a.sa_len = scale_a_len; a.sb = scale_b; a.sb_len = scale_b_len;
+    a.bias = bias; a.bias_dtype = bias_dtype; a.sr = scale_result;
+    a.ws = const_cast<void**>(C_dsts); a.ws_bytes = (size_t)n_dst * sizeof(void*); a.st = (cudaStream_t)stream;
+    a.store_mc = 3 | (n_dst << 8);
+    a.sig = &sig;
+    int rc = validate(a);
+    if (rc != FP8B_OK) return rc;
+    if (M == 0 || N == 0) return FP8B_ERR_UNSUPPORTED;        // an empty shard cannot signal: the caller uses fp8b_peer_signal
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    if (!tcgen05_supported(a)) return FP8B_ERR_UNSUPPORTED;
+    return launch_gemm_tcgen05(a);
+}
+
+extern "C" int fp8b_peer_wait(const uint64_t* flags, int world, int rank, uint64_t epoch, void* stream)
+{
+    if (!flags || world < 2 || world > 8 || rank < 0 || rank >= world) return FP8B_ERR_INVALID;
+    if (!device_info().ok) return FP8B_ERR_NO_DEVICE;
+    return launch_peer_wait(flags, world, rank, epoch, (cudaStream_t)stream);
+}
+
 extern "C" int fp8b_scaled_mm_push_supported(int out_dtype, int M, int N, int K, int64_t ldc, const void* A, const void* B,
                                              const void* C)
 {

@@ -101,7 +101,15 @@ template <int BN, int CG, int MODE = kStDirect> struct GemmCfg {
     static_assert((2 * kStages + 4 + 2 * kStoreSlots) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
 
-struct StoreMaps { CUtensorMap m[kMaxDst]; };    // kStTma: one byte-typed map per destination buffer
+// kStTma / kStWide: one tensor map per destination buffer, plus the optional completion signal: when the last CTA of
+// the grid has pushed its last box, it stores `epoch` into sig[d] for every peer d (a flag in the PEER's memory).
+struct StoreMaps {
+    CUtensorMap m[kMaxDst];
+    unsigned long long* sig[kMaxDst];        // sig[d]: where to tell destination d "rank's boxes have landed" (null: nobody)
+    unsigned int* cta_counter;               // device counter, 0 between launches (reset by the last CTA)
+    unsigned long long epoch;
+    int n_sig;                               // 0: no signalling (the caller orders ranks itself)
+};
 struct NoStoreMaps { int unused; };
 template <int MODE> struct StoreMapsOf { using type = NoStoreMaps; };
 template <> struct StoreMapsOf<kStTma> { using type = StoreMaps; };
@@ -380,6 +388,10 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+
+    // push modes: let the kernel that follows on the stream (fp8b_peer_wait, launched with the PDL attribute) become
+    // resident now, so that its launch latency is behind it when the peers' completion flags arrive
+    if (is_push<MODE>()) pdl_launch_dependents();
 
     if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -848,6 +860,49 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tc_fence_after();
         if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
+    if constexpr (is_push<MODE>()) {
+        // Completion signal (fused closing barrier, send side).  Every store warp has waited for its bulk groups
+        // (writes performed) before the CTA-wide barrier above.  One thread per CTA publishes that system-wide and
+        // counts the CTA in; the last CTA of the grid tells every peer, with a release store into the PEER's flag word,
+        // that all of this rank's boxes have landed.  fp8b_peer_wait on the peer acquires that flag.
+        if (smaps.n_sig > 0 && threadIdx.x == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");               // async-proxy (TMA) writes before generic-proxy signalling
+            __threadfence_system();
+            const unsigned int done = atomicAdd(smaps.cta_counter, 1u) + 1u;
+            if (done == gridDim.x) {
+                __threadfence_system();
+                *smaps.cta_counter = 0u;                                     // ready for the next launch (stream-ordered)
+                for (int d = 0; d < smaps.n_sig; ++d)
+                    if (smaps.sig[d])
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(smaps.sig[d]), "l"(smaps.epoch) : "memory");
+            }
+        }
+    }
+}
+
+// Receive side of the fused closing barrier: returns (completes) when every peer's flag has reached `epoch`, i.e. every
+// peer's push kernel has finished writing into this rank's buffer -- and, through griddepcontrol.wait, when this rank's own
+// push kernel (its predecessor on the stream) has completed.  Launched with the PDL attribute: it is resident and
+// polling long before the flags arrive.  A peer that never signals trips the watchdog instead of hanging the GPU.
+__global__ void fp8_peer_wait_kernel(const unsigned long long* __restrict__ flags, int world, int rank, unsigned long long epoch)
+{
+    const int r = threadIdx.x;
+    if (r < world && r != rank) {
+        unsigned long long t0 = 0, v = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        unsigned int spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+            if (v >= epoch) break;
+            if ((++spins & 0xFFF) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) __trap();                      // 20 s
+            }
+        }
+    }
+    __syncthreads();
+    pdl_wait();                                                              // our own push kernel has completed and flushed
 }
 
 
@@ -937,6 +992,23 @@ static bool tma_store_ok(const MMArgs& a, void* const* dsts, int n_dst)
     return true;
 }
 
+static void fill_signal(StoreMaps& sm, const MMArgs& a)
+{
+    sm.n_sig = 0; sm.cta_counter = nullptr; sm.epoch = 0;
+    for (int d = 0; d < kMaxDst; ++d) sm.sig[d] = nullptr;
+    if (!a.sig) return;
+    sm.n_sig = a.store_mc >> 8;
+    for (int d = 0; d < sm.n_sig; ++d) sm.sig[d] = reinterpret_cast<unsigned long long*>(a.sig->flags[d]);
+    sm.cta_counter = a.sig->cta_counter;
+    sm.epoch = a.sig->epoch;
+}
+
+int launch_peer_wait(const uint64_t* flags, int world, int rank, uint64_t epoch, cudaStream_t st)
+{
+    return launch_ex(fp8_peer_wait_kernel, dim3(1), dim3(32), 0, st, 1, 1, /*pdl=*/true,
+                     reinterpret_cast<const unsigned long long*>(flags), world, rank, (unsigned long long)epoch);
+}
+
 template <int BN, int CG, int MODE = kStDirect>
 static int launch_tcgen05_cfg(const MMArgs& a)
 {
@@ -998,6 +1070,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
             if (!get_tensor_map(&smaps.m[d], dsts[d], (uint64_t)a.M, (uint64_t)a.N * esz, (uint64_t)a.ldc * esz, 128, 128))
                 return FP8B_ERR_CUDA;
         for (int d = n_dst; d < kMaxDst; ++d) smaps.m[d] = smaps.m[0];
+        fill_signal(smaps, a);
     } else if constexpr (MODE == kStWide) {  // same arguments; 16-bit outputs, one linear box per tile
         const int n_dst = a.store_mc >> 8;
         void* const* dsts = static_cast<void* const*>(a.ws);
@@ -1008,6 +1081,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
             if (!get_tensor_map(&smaps.m[d], dsts[d], (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ldc * 2, 128, BN, 2, false))
                 return FP8B_ERR_CUDA;
         for (int d = n_dst; d < kMaxDst; ++d) smaps.m[d] = smaps.m[0];
+        fill_signal(smaps, a);
     } else {
         smaps.unused = 0;
 #ifdef FP8B_PROFILE

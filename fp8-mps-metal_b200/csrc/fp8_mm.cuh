@@ -8,6 +8,13 @@
 
 namespace fp8b {
 
+// optional completion signal of the push kernel (fp8b_scaled_mm_push_signal)
+struct PushSignal {
+    uint64_t* flags[8];            // flags[d]: the word in destination d's memory to set (null for this rank itself)
+    unsigned int* cta_counter;     // local device counter, zero between launches
+    uint64_t epoch;
+};
+
 struct MMArgs {
     const uint8_t* A;      // (M,K) row-major
     const uint8_t* B;      // (N,K) row-major
@@ -23,6 +30,7 @@ struct MMArgs {
     int store_mc;          // tcgen05 kernel only: C is a multicast address (multimem.st)
     cudaStream_t st;
     int a_fmt = 0, b_fmt = 0;   // operand formats (FP8B_E4M3FN / FP8B_E5M2); host-side routing only
+    const PushSignal* sig = nullptr;   // push kernel only
     int chain_pdl = 0;     // GEMV only: the predecessor on the stream is our own quantise kernel (never writes B),
                            // so launch with PDL and prefetch B before griddepcontrol.wait
 };
@@ -38,6 +46,7 @@ bool gemv_mma_supported(const MMArgs& a);
 int launch_gemv_mma(const MMArgs& a);
 int launch_gemm_simt(const MMArgs& a);
 int launch_gemm_tcgen05(const MMArgs& a);
+int launch_peer_wait(const uint64_t* flags, int world, int rank, uint64_t epoch, cudaStream_t st);
 
 // ---- fused epilogue -----------------------------------------------------------------------
 // out = cast( (((acc * sa) * sb) [+ bias]) [* scale_result] ), every step a separately rounded

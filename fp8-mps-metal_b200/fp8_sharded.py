@@ -87,6 +87,10 @@ class ShardedScaledMM:
             assert bias.numel() == self.n1 - self.n0
             self.bias = bias.reshape(-1).contiguous()
         self._symm = None
+        self._sig = None
+        #: push mode: fuse the closing barrier into the exchange (kernel-side signal + a PDL wait kernel) instead of a
+        #: separate symmetric-memory barrier kernel after it
+        self.fused_barrier = True
 
     # ------------------------------------------------------------------ local compute
     def local(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16, out=None) -> torch.Tensor:
@@ -254,11 +258,42 @@ class ShardedScaledMM:
         key, pair, turn = self._symm_buffers(M, odt, x_u8.device)
         buf, hdl = pair[turn]
         self._symm = (key, pair, turn ^ 1)
+        lib = fp8_mps_native._get_lib()
+        if self.fused_barrier and self._all_shards_nonempty():
+            # closing barrier fused into the exchange: the push kernel's last CTA stores this call's epoch into every
+            # peer's flag word; fp8b_peer_wait (one warp, programmatic dependent launch, already resident) returns when
+            # every peer's flag has arrived and this rank's own kernel has completed
+            sig = self._signal_state(x_u8.device)
+            sig["epoch"] += 1
+            lib.fp8_scaled_mm_push(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf, self._push_order(turn, hdl),
+                                   int(self.n0), sig["order"], sig["counter"], sig["epoch"], sig["flags"], self.rank)
+            return buf
         if self.n1 > self.n0:
-            fp8_mps_native._get_lib().fp8_scaled_mm_push(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
-                                                         self._push_order(turn, hdl), int(self.n0))
+            lib.fp8_scaled_mm_push(x_u8, self.weight, scale_a, self.scale_b, self.bias, buf,
+                                   self._push_order(turn, hdl), int(self.n0))
         hdl.barrier(channel=0)                                  # every rank's boxes have landed everywhere
         return buf
+
+    def _all_shards_nonempty(self) -> bool:
+        return all(shard_bounds(self.N, self.world, r, self.align)[1] > shard_bounds(self.N, self.world, r, self.align)[0]
+                   for r in range(self.world))
+
+    def _signal_state(self, device):
+        """Symmetric flag words for the fused barrier: flags[r] on this rank is written by rank r.  Epochs only grow."""
+        if self._sig is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            pg = self.group if self.group is not None else dist.group.WORLD
+            flags = symm_mem.empty(16, dtype=torch.int64, device=device)
+            flags.zero_()
+            hdl = symm_mem.rendezvous(flags, pg)
+            hdl.barrier(channel=0)                              # every rank's zeros are in place before anyone signals
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            order = []
+            for d in range(self.world):                          # same order as _push_order: own buffer first
+                r = (self.rank + d) % self.world
+                order.append(0 if r == self.rank else ptrs[r] + 8 * self.rank)
+            self._sig = dict(flags=flags, hdl=hdl, counter=torch.zeros(1, dtype=torch.int32, device=device), order=order, epoch=0)
+        return self._sig
 
     def _push_order(self, turn, hdl):
         """Destination base addresses for this buffer of the pair: own buffer first, then the ring of peers starting

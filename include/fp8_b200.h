@@ -343,6 +343,25 @@ FP8B_API int fp8b_scaled_mm_push(const uint8_t* A, const uint8_t* B, void* const
                         const float* scale_b, int scale_b_len,
                         const void* bias, int bias_dtype,
                         const float* scale_result, void* stream);
+/*
+ * fp8b_scaled_mm_push with the closing barrier's SEND side fused into the kernel: when the last CTA of the grid has
+ * pushed its last box it stores `epoch` (release, system scope) into signal_flags[d] for every destination d --
+ * a 64-bit word in destination d's memory (its slot for this rank in a symmetric flag array; NULL for this rank
+ * itself).  cta_counter: a device uint32 that is zero between launches.  Epochs must increase from call to call.
+ * The RECEIVE side is fp8b_peer_wait: a one-warp kernel, launched with programmatic dependent launch so that it is
+ * resident and polling while the push kernel still runs; it completes when flags[r] >= epoch for every r != rank
+ * (every peer's boxes have landed here) and this rank's own push kernel has completed.  Together they replace the
+ * separate barrier kernel after the exchange (8 us at w = 2) by ~one NVLink round trip.  A peer that never signals
+ * trips a 20 s watchdog (the kernel traps) instead of hanging the GPU.
+ */
+FP8B_API int fp8b_scaled_mm_push_signal(const uint8_t* A, const uint8_t* B, void* const* C_dsts, int n_dst,
+                               int out_dtype, int M, int N, int K, int64_t ldc,
+                               const float* scale_a, int scale_a_len,
+                               const float* scale_b, int scale_b_len,
+                               const void* bias, int bias_dtype, const float* scale_result,
+                               uint64_t* const* signal_flags, uint32_t* cta_counter, uint64_t epoch, void* stream);
+FP8B_API int fp8b_peer_wait(const uint64_t* flags, int world, int rank, uint64_t epoch, void* stream);
+
 /* 1 when fp8b_scaled_mm_push can serve this shape and alignment (a pure function: every rank of a group can
  * evaluate it for every other rank's shard before anyone launches). */
 FP8B_API int fp8b_scaled_mm_push_supported(int out_dtype, int M, int N, int K, int64_t ldc, const void* A, const void* B,

@@ -79,6 +79,27 @@ for K in (64, 3072):
         out.append(f"GEMM+push K={K:4d} {name:14s}: {us:7.1f} us  {shard_bytes * (len(dsts) - (1 if name != 'peer only' else 0)) / us / 1e3:6.0f} GB/s to peers")
     us = timed(lambda: lin.local(a, sa, torch.bfloat16))
     out.append(f"GEMM K={K:4d} st.global epilogue, local shard: {us:7.1f} us")
+# the exchange path alone (K = 64, peer only) under the kernel's knobs: tile shape, tile order, box form
+K = 64
+g = torch.Generator(device=dev).manual_seed(3)
+a = torch.randint(0, 120, (M, K), dtype=torch.uint8, device=dev, generator=g)
+n0, n1, _ = shard_bounds(N, world, rank)
+w = torch.randint(0, 120, (n1 - n0, K), dtype=torch.uint8, device=dev, generator=g)
+lin = ShardedScaledMM(w, sb, None, weight_is_shard=True, full_N=N)
+key, pair, turn = lin._symm_buffers(M, torch.bfloat16, dev)
+b2, h2 = pair[0]
+order = lin._push_order(0, h2)
+lib = nat._get_lib()
+for cfg in (3, 4, 2):
+    for raster in (1, 2):
+        for store in (4, 3):
+            lib.set_option(16, cfg); lib.set_option(24, raster); lib.set_option(20, store)
+            try:
+                us = timed(lambda: lib.fp8_scaled_mm_push(a, w, sa, sb, None, b2, order[1:2], int(n0)))
+                out.append(f"K=64 peer only cfg{cfg} raster{raster} store{store}: {us:7.1f} us {M * (n1 - n0) * 2 / us / 1e3:6.0f} GB/s")
+            except Exception as e:
+                out.append(f"K=64 cfg{cfg} raster{raster} store{store}: {str(e)[:80]}")
+lib.set_option(16, -1); lib.set_option(24, -1); lib.set_option(20, -1)
 if rank == 0:
     print(f"world {world}")
     print("\n".join(out), flush=True)

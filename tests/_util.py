@@ -80,6 +80,11 @@ def capi():
         L.fp8b_scaled_mm_push.restype = i32
         L.fp8b_scaled_mm_push.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32,
                                           vp, vp]
+        L.fp8b_scaled_mm_push_signal.restype = i32
+        L.fp8b_scaled_mm_push_signal.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i64, vp, i32, vp, i32, vp, i32, vp,
+                                                 vp, vp, i64, vp]
+        L.fp8b_peer_wait.restype = i32
+        L.fp8b_peer_wait.argtypes = [vp, i32, i32, i64, vp]
         L.fp8b_scaled_mm_push_supported.restype = i32
         L.fp8b_scaled_mm_push_supported.argtypes = [i32, i32, i32, i32, i64, vp, vp, vp]
     _lib = L
