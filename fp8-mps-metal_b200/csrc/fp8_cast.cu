@@ -768,6 +768,24 @@ static int launch_decode_vec(const uint8_t* in, void* out, size_t n, const float
         return launch_ex(fp8_to_wide_tma_kernel<OUT, SCALED, FMT>, dim3((unsigned)grid), dim3(kTmaCvtThreads + 32), (size_t)kSmem, st, 1, 1,
                          pdl, in, out, n, scale);
     }
+#ifdef FP8B_PROFILE
+    // launch-shape sweep for the write-heavy direction (profiling builds only): CAST_SHAPE 11.. = threads x unroll x CTAs/SM
+    if constexpr (OUT == FP8B_F16 && !SCALED && FMT == 0) {
+        const int sms = device_info().sm_count;
+        switch (mode) {
+            case 11: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 8, FMT>, dim3(sms * 2), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 12: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 8, FMT>, dim3(sms * 4), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 13: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 4, FMT>, dim3(sms * 2), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 14: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 1024, 4, FMT>, dim3(sms), dim3(1024), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 15: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 16, FMT>, dim3(sms), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 16: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 8, FMT>, dim3(sms * 2), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 17: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 4, FMT>, dim3(sms * 8), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 18: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 128, 8, FMT>, dim3(sms * 8), dim3(128), 0, st, 1, 1, pdl, in, out, n, scale);
+            case 19: return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 1024, 8, FMT>, dim3(sms), dim3(1024), 0, st, 1, 1, pdl, in, out, n, scale);
+            default: break;
+        }
+    }
+#endif
     if (c.big) return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 512, 8, FMT>, dim3(c.grid), dim3(512), 0, st, 1, 1, pdl, in, out, n, scale);
     return launch_ex(fp8_to_wide_kernel<OUT, SCALED, 256, 4, FMT>, dim3(c.grid), dim3(256), 0, st, 1, 1, pdl, in, out, n, scale);
 }

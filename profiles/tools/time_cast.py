@@ -22,9 +22,11 @@ outs = {m: torch.empty(total, dtype=torch.float16, device=dev) for m in (0, 3, 4
 offs = [0]
 for s in sizes: offs.append(offs[-1] + s)
 print(f"{len(sizes)} tensors, {total/1e9:.2f} G elements, {3*total/1e9:.1f} GB traffic per sweep", flush=True)
+SWEEP = [int(x) for x in os.environ.get("CAST_SWEEP", "").split(",") if x]      # profiling library only: modes 11..19
 for out_dt, code, esz in ((torch.float16, 1, 2), (torch.bfloat16, 2, 2), (torch.float32, 0, 4)):
     res = {}
-    for mode in (0, 3, 4):
+    modes = (0, 3, 4) + (tuple(SWEEP) if out_dt == torch.float16 else ())
+    for mode in modes:
         h = torch.empty(total, dtype=out_dt, device=dev)
         L.fp8b_set_option(19, mode if mode else -1)
         def sweep():
@@ -45,8 +47,8 @@ for out_dt, code, esz in ((torch.float16, 1, 2), (torch.bfloat16, 2, 2), (torch.
             best = min(best, e0.elapsed_time(e1) / 2)
         res[mode] = ((1 + esz) * total / (best * 1e-3) / 1e9, h)
     L.fp8b_set_option(19, -1)
-    same = all(torch.equal(res[0][1].view(torch.uint8), res[m][1].view(torch.uint8)) for m in (3, 4))
-    print(f"fp8->{str(out_dt)[6:]:9s}: " + "  ".join(f"mode{m} {res[m][0]:6.0f} GB/s" for m in (0, 3, 4)) + f"  bit-equal {same}", flush=True)
+    same = all(torch.equal(res[0][1].view(torch.uint8), res[m][1].view(torch.uint8)) for m in modes[1:])
+    print(f"fp8->{str(out_dt)[6:]:9s}: " + "  ".join(f"mode{m} {res[m][0]:6.0f} GB/s" for m in modes) + f"  bit-equal {same}", flush=True)
     del res
     torch.cuda.empty_cache()
 # one big tensor and a small one with a ragged tail
