@@ -849,9 +849,9 @@ def main():
                 entry["tflops_total"] = round(C4_FLOPS / (entry["us_per_call"] * 1e-6) / 1e12, 1)
                 entry["launches_per_step"] = int((L.fp8b_launch_count() - n0_l) // steps)
                 entry["_ms"], entry["_t0"], entry["_t1"] = t_ms, tw0, tw1
-            except Exception as e:
-                entry["error"] = repr(e)[:200]
-                entry["parity"] = False
+            except Exception as e:                 # e.g. no NVLS multicast on this system: the plan did not run at all
+                entry["unavailable"] = repr(e)[:200]
+                entry["parity"] = None
             sharded["plans"][name] = entry
         # compute only (no exchange): this rank's shard through the plain kernel
         def step_local():
@@ -882,7 +882,7 @@ def main():
                                        "is bound by that exchange, not by the tensor pipe"}
         sharded["best_plan"] = min((k for k, v in sharded["plans"].items() if "us_per_call" in v and v.get("parity")),
                                    key=lambda k: sharded["plans"][k]["us_per_call"], default=None)
-        sharded["parity"] = {k: bool(v.get("parity")) for k, v in sharded["plans"].items()}
+        sharded["parity"] = {k: v.get("parity") for k, v in sharded["plans"].items()}      # true / false / null = plan unavailable here
 
     ms = max_over_ranks(torch, dist, ms) if n_gpus == 1 else ms
     ms_per_step = ms / steps

@@ -46,15 +46,16 @@ n = 1 << 28; cnt = total // n
 es = make_spans([(src.data_ptr() + 2 * i * n, q.data_ptr() + i * n, n) for i in range(cnt)])
 ds = make_spans([(q.data_ptr() + i * n, h.data_ptr() + 2 * i * n, n) for i in range(cnt)])
 for shape in (1, 2):
-    os.environ["FP8B_CAST_SHAPE"] = str(shape)
+    L.fp8b_set_option(19, shape)                 # FP8B_OPT_TUNE_CAST_SHAPE (round 2: knobs are library options)
     e = 3.0 * total / timeit(lambda: L.fp8b_encode_batch(es, cnt, 2, sp())) / 1e6
     d = 3.0 * total / timeit(lambda: L.fp8b_dequant_batch(ds, cnt, 1, sp())) / 1e6
     print(f"FP8B_CAST_SHAPE={shape}: encode {e:7.0f}  dequant {d:7.0f} GB/s", flush=True)
+L.fp8b_set_option(19, -1)
 
 # amax (read-only pass of fp8_quantize): 2 B/element
 scales = torch.empty(2, device=dev); scratch = torch.zeros(1, dtype=torch.int32, device=dev)
 for lib, tag in ((L, "current"),):
     for cap in (2, 3, 4, 6, 8):
-        os.environ["FP8B_AMAX_CAP"] = str(cap)
+        lib.fp8b_set_option(23, cap)             # FP8B_OPT_TUNE_AMAX_CAP
         ms = timeit(lambda: lib.fp8b_amax_scale(P(src.data_ptr()), 2, total, P(scales.data_ptr()), P(scales.data_ptr() + 4), P(scratch.data_ptr()), sp()))
         print(f"amax bf16 {tag} cap {cap}/SM: {2.0 * total / ms / 1e6:7.0f} GB/s", flush=True)

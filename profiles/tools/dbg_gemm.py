@@ -1,3 +1,6 @@
+"""Per-tile clock64 timeline of the tcgen05 kernel.  Needs the PROFILING build of the library (the shipped one has no such knob):
+    FP8B_BUILD_PROFILE=1 python fp8-mps-metal_b200/build.py
+    FP8B_LIB=profiles/tools/bin/libfp8_b200_profile.so FP8B_GEMM_STORE=1 python profiles/tools/dbg_gemm.py"""
 import ctypes, os, sys
 ROOT=os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0,ROOT+'/fp8-mps-metal_b200'); sys.path.insert(0,ROOT+'/tests')

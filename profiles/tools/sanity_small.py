@@ -18,14 +18,14 @@ one = torch.ones(1, device=dev)
 lib = n._get_lib()
 for (M, K, N) in [(1, 512, 300), (1, 4096, 64), (3, 64, 40), (4, 1024, 100), (16, 256, 33), (2, 37, 5), (1, 2048, 400)]:
     for impl in ("1", "2", "3"):
-        os.environ["FP8B_GEMV_IMPL"] = impl
+        lib.set_option(17, int(impl))            # FP8B_OPT_TUNE_GEMV_IMPL
         lib.fp8_scaled_mm_fused(u8(M, K), u8(N, K), one, one, torch.randn(N, device=dev).bfloat16(), one, torch.bfloat16, 1, None)
-os.environ.pop("FP8B_GEMV_IMPL")
+lib.set_option(17, -1)
 for cfg in ("1", "2", "3", "4", "5"):
-    os.environ["FP8B_GEMM_CFG"] = cfg
+    lib.set_option(16, int(cfg))                 # FP8B_OPT_TUNE_GEMM_CFG
     for (M, K, N) in [(300, 336, 520), (129, 64, 257)]:
         lib.fp8_scaled_mm_fused(u8(M, K), u8(N, K), torch.rand(M, device=dev), torch.rand(N, device=dev), None, None, None, 2, None)
-os.environ.pop("FP8B_GEMM_CFG")
+lib.set_option(16, -1)
 lib.fp8_scaled_mm_fused(u8(2304, 128, ), u8(2500, 128), one, one, None, None, torch.bfloat16, 2, None)     # last-wave split
 lib.fp8_scaled_mm_fused(u8(70, 50), u8(33, 50), one, one, None, None, None, 3, None)                      # SIMT
 torch.cuda.synchronize()

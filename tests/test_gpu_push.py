@@ -172,3 +172,36 @@ def test_tile_raster_orders_agree(tune, M, K, N, odt):
         assert torch.equal(outs[0], c)
     ref = o.scaled_mm(A, B, np.full(1, 0.01, np.float32), np.full(1, 0.01, np.float32), None, None, dt_name(odt))
     assert o.rel_rmse(to_np(outs[0]), ref) <= TOL[dt_name(odt)]
+
+
+def test_push_signal_and_peer_wait_on_one_gpu():
+    """The fused closing barrier through the C ABI, both ends on one GPU: fp8b_scaled_mm_push_signal (two local
+    destinations standing in for this rank and a peer) stores the epoch into the "peer's" flag word when its last box
+    has landed; fp8b_peer_wait -- launched with PDL, resident while the GEMM runs -- returns only then.  (Safe on one GPU:
+    the waiter depends on the GEMM, never the other way round.)  Epochs grow; the CTA counter resets itself."""
+    import ctypes
+    from _util import dt_code, p, stream_ptr
+    L = capi()
+    M, K, N = 1024, 512, 1536
+    A, B = _bytes((M, K), 31), _bytes((N, K), 32)
+    tA, tB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
+    s = torch.full((1,), 0.01, device=DEV)
+    flags = torch.zeros(16, dtype=torch.int64, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    rc, direct = mm_capi(tA, tB, s, s, None, None, torch.bfloat16, ALGO_TCGEN05)
+    assert rc == 0
+    for epoch in (1, 2, 3):
+        d0 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        d1 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        dsts = (ctypes.c_void_p * 2)(d0.data_ptr(), d1.data_ptr())
+        sig = (ctypes.c_void_p * 2)(None, flags.data_ptr() + 8 * 1)          # "peer" 1's word on "rank" 0: here, local memory
+        rc = L.fp8b_scaled_mm_push_signal(p(tA), p(tB), dsts, 2, dt_code(torch.bfloat16), M, N, K, N, p(s), 1, p(s), 1, None, 0, None,
+                                          sig, p(counter), epoch, stream_ptr())
+        assert rc == 0, L.fp8b_status_string(rc)
+        assert L.fp8b_peer_wait(p(flags), 2, 0, epoch, stream_ptr()) == 0
+        after = flags.clone()                                                   # stream-ordered behind the wait kernel
+        torch.cuda.synchronize()
+        assert int(after[1]) == epoch and int(counter[0]) == 0
+        assert torch.equal(d0, direct) and torch.equal(d1, direct)
+    assert L.fp8b_peer_wait(None, 2, 0, 1, stream_ptr()) == -1
+    assert L.fp8b_peer_wait(p(flags), 9, 0, 1, stream_ptr()) == -1
