@@ -83,8 +83,8 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
     const uint8_t* x0 = p.A + (size_t)(xa_ok ? g : 0) * K + 16 * t;
     const uint8_t* x1 = p.A + (size_t)(xb_ok ? g + 8 : 0) * K + 16 * t;
 
-    // two accumulator sets per activation tile: the two MMAs of a k-step are independent, which halves the chain of
-    // dependent tensor-core instructions each warp has to get through once its loads have landed
+    // M <= 8: two accumulator sets, so the two MMAs of a k-step are independent -- halves the chain of dependent
+    // tensor-core instructions each warp has to get through once its loads have landed (C3: 6.08 -> 5.83 us)
     float c[NB][4], d[NB][4];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
@@ -131,11 +131,14 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
         load_x(nxa, nxb, kb + 64 * BATCH);
 #pragma unroll
         for (int s = 0; s < BATCH; ++s) {
-            mma_f8_m16n8k32<WF, XF>(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
-            mma_f8_m16n8k32<WF, XF>(d[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
-            if (NB == 2) {
-                mma_f8_m16n8k32<WF, XF>(c[1], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xb[s].x, xb[s].y);
-                mma_f8_m16n8k32<WF, XF>(d[1], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xb[s].z, xb[s].w);
+            if (NB == 1) {
+                mma_f8_m16n8k32<WF, XF>(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
+                mma_f8_m16n8k32<WF, XF>(d[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
+            } else {                     // two activation tiles are two independent chains already (and four sets spill occupancy)
+                mma_f8_m16n8k32<WF, XF>(c[0], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xa[s].x, xa[s].y);
+                mma_f8_m16n8k32<WF, XF>(c[NB - 1], wa[s].x, wb[s].x, wa[s].y, wb[s].y, xb[s].x, xb[s].y);
+                mma_f8_m16n8k32<WF, XF>(c[0], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xa[s].z, xa[s].w);
+                mma_f8_m16n8k32<WF, XF>(c[NB - 1], wa[s].z, wb[s].z, wa[s].w, wb[s].w, xb[s].z, xb[s].w);
             }
         }
 #pragma unroll
@@ -148,8 +151,10 @@ fp8_gemv_mma_kernel(const GemvMmaParams p)
     // fragment -> shared: c0:(g, 2t) c1:(g, 2t+1) c2:(g+8, 2t) c3:(g+8, 2t+1)
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
+        if (NB == 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) c[b][i] += d[b][i];
+            for (int i = 0; i < 4; ++i) c[b][i] += d[b][i];
+        }
         part[warp][g][8 * b + 2 * t] = c[b][0];
         part[warp][g][8 * b + 2 * t + 1] = c[b][1];
         part[warp][g + 8][8 * b + 2 * t] = c[b][2];
