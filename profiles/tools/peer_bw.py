@@ -100,6 +100,13 @@ for cfg in (3, 4, 2):
             except Exception as e:
                 out.append(f"K=64 cfg{cfg} raster{raster} store{store}: {str(e)[:80]}")
 lib.set_option(16, -1); lib.set_option(24, -1); lib.set_option(20, -1)
+# does the destination ROW PITCH matter (NVLink / memory address interleaving)?  Same K = 64 push into wider buffers.
+for pad in (0, 64, 128, 256, 320, 1024, 2048):
+    wide_buf = symm_mem.empty((M, N + pad), dtype=torch.bfloat16, device=dev)
+    wh = symm_mem.rendezvous(wide_buf, dist.group.WORLD)
+    ptrs = [int(p_) for p_ in wh.buffer_ptrs]
+    us = timed(lambda: lib.fp8_scaled_mm_push(a, w, sa, sb, None, wide_buf, [ptrs[(rank + 1) % world]], int(n0)))
+    out.append(f"K=64 peer only, destination pitch {2 * (N + pad):6d} B: {us:7.1f} us {M * (n1 - n0) * 2 / us / 1e3:6.0f} GB/s")
 if rank == 0:
     print(f"world {world}")
     print("\n".join(out), flush=True)
