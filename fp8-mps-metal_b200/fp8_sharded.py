@@ -89,8 +89,10 @@ class ShardedScaledMM:
         self._symm = None
         self._sig = None
         #: push mode: fuse the closing barrier into the exchange (kernel-side signal + a PDL wait kernel) instead of a
-        #: separate symmetric-memory barrier kernel after it
-        self.fused_barrier = True
+        #: separate symmetric-memory barrier kernel after it.  Measured (profiles/r2_scaling.md): w = 2 101.1 vs 102.7 us,
+        #: w = 4 144.9 vs 145.0 us, w = 8 174.8 vs 166.9 us (seven system-scope release stores from one thread, and the skew
+        #: between eight ranks, cost more than the barrier kernel) -- so it is the default for two ranks only.
+        self.fused_barrier = self.world <= 2
 
     # ------------------------------------------------------------------ local compute
     def local(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16, out=None) -> torch.Tensor:

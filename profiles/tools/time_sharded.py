@@ -78,13 +78,17 @@ def compute_rasterN():
     finally:
         nat._get_lib().set_option(24, -1)
 variants["compute_only_rasterN"] = compute_rasterN
-def push_symm_barrier():
-    lin.fused_barrier = False
-    try:
-        lin(a, sa, torch.bfloat16, mode="push")
-    finally:
-        lin.fused_barrier = True
-variants["push_symm_barrier"] = push_symm_barrier
+def mk_barrier(fused):
+    def run():
+        keep = lin.fused_barrier
+        lin.fused_barrier = fused
+        try:
+            lin(a, sa, torch.bfloat16, mode="push")
+        finally:
+            lin.fused_barrier = keep
+    return run
+variants["push_symm_barrier"] = mk_barrier(False)
+variants["push_fused_barrier"] = mk_barrier(True)
 only = os.environ.get("ONLY")
 if only:
     variants = {k: v for k, v in variants.items() if k in only.split(",")}
