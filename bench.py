@@ -246,7 +246,27 @@ def max_over_ranks(torch, dist, ms):
 
 # --------------------------------------------------------------------------- CPU baseline (oracle port)
 
+def _use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host cores it may."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
 def _cpu_c4_inputs():
+    _use_all_host_cores()
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import fp8_oracle as o
@@ -859,9 +879,16 @@ def main():
                 lin.local(a, inv_a, torch.bfloat16)
         ms_l, _, _, _ = time_graph(torch, step_local, steps, warmup, dist)
         sharded["shard_gemm_only_us"] = round(max_over_ranks(torch, dist, ms_l) / steps * 1e3 / SETS, 2)
-        head = sharded["plans"]["push_fused"]
-        if "us_per_call" not in head:
-            raise RuntimeError(f"push plan failed: {head}")
+        # the headline is the default plan of ShardedScaledMM (push); should it be unavailable on a box, the first row-major
+        # plan that ran takes its place and the line says so -- a missing JSON line helps nobody
+        head_name = next((k for k in ("push_fused", "multicast_fused", "peer_store_fused", "allgather_row_major")
+                          if "us_per_call" in sharded["plans"][k]), None)
+        if head_name is None:
+            raise RuntimeError(f"no exchange plan ran: {sharded['plans']}")
+        sharded["headline_plan"] = head_name
+        e2e_mode = {"push_fused": "push", "multicast_fused": "multicast", "peer_store_fused": "peers",
+                    "allgather_row_major": "allgather"}[head_name]
+        head = sharded["plans"][head_name]
         ms, t0, t1 = head.pop("_ms"), head.pop("_t0"), head.pop("_t1")
         for e in sharded["plans"].values():
             for k in ("_ms", "_t0", "_t1"):
@@ -869,7 +896,8 @@ def main():
         launches_per_step = head["launches_per_step"]
         clocks = sampler.summary(t0, t1)
         kernel_us = head["us_per_call"]
-        kernel_name = "fp8b::fp8_gemm_tcgen05_kernel<BN,2,2> (tcgen05 GEMM + TMA push to every rank), incl. the closing barrier"
+        kernel_name = ("fp8b::fp8_gemm_tcgen05_kernel<BN,2,2> (tcgen05 GEMM + TMA push to every rank), incl. the closing barrier"
+                       if head_name == "push_fused" else f"exchange plan {head_name}")
         floor_link = (n_gpus - 1) / n_gpus * C4_OUT_BYTES / (NVLINK_GBS * 1e9) * 1e6
         floor_link_meas = (n_gpus - 1) / n_gpus * C4_OUT_BYTES / (NVLINK_MEASURED_GBS * 1e9) * 1e6
         floor_mma = C4_FLOPS / n_gpus / (fp8_peak * 1e12) * 1e6
@@ -929,10 +957,10 @@ def main():
                 else:
                     dA.copy_(hA, non_blocking=True)
                 lin.weight.copy_(hW, non_blocking=True)
-                y = lin(dA, inv_a, torch.bfloat16, mode="push")
+                y = lin(dA, inv_a, torch.bfloat16, mode=e2e_mode)
                 hC.copy_(y[r0_:r1_], non_blocking=True)
             h2d, d2h = hA_slab.numel() + hW.numel(), hC.numel() * 2
-            call = ("ShardedScaledMM(W8, scale_b)(A8, scale_a, torch.bfloat16, mode='push'): this rank's 1/N row slab of A "
+            call = (f"ShardedScaledMM(W8, scale_b)(A8, scale_a, torch.bfloat16, mode='{e2e_mode}'): this rank's 1/N row slab of A "
                     "(all-gathered over NVLink) and its W shard copied from pinned host memory, this rank's 1/N row slab of the "
                     "assembled (M,N) result copied back, every call")
         for _ in range(3):
