@@ -718,25 +718,26 @@ def emit(line):
 
 
 def pin_to_gpu_numa_node(torch, index):
-    """Best effort: run this rank's host thread (and so first-touch its pinned buffers) on the CPUs of the NUMA node
-    the GPU hangs off, so that N ranks' host<->device copies do not all cross one memory controller."""
+    """Best effort: run this rank's host thread (and so first-touch its pinned buffers) on the CPUs NVML names as local
+    to the GPU, so that N ranks' host<->device copies do not all cross one memory controller.  Inside a container the
+    cpuset may not contain them; then nothing is changed and the line says so."""
     try:
-        pr = torch.cuda.get_device_properties(index)
-        bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
-        if not os.path.exists(f"/sys/bus/pci/devices/{bus}"):
-            return "pci device not visible in sysfs"
-        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
-        if node < 0:
-            return "numa node unknown"
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        allowed = os.sched_getaffinity(0) & cpus
-        if allowed:
-            os.sched_setaffinity(0, allowed)
-            return f"node {node}, {len(allowed)} cpus"
-        return f"node {node} outside this process's cpuset"
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        ideal = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        both = ideal & allowed
+        if not ideal:
+            return "no affinity reported"
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            return f"pinned to {len(both)} of {len(allowed)} cpus local to the GPU"
+        if both == allowed:
+            return f"all {len(allowed)} allowed cpus are local to the GPU"
+        return "GPU-local cpus outside this process's cpuset"
     except Exception as e:
         return f"not pinned: {type(e).__name__}"
 
