@@ -60,7 +60,10 @@ constexpr int kMaxDst = 8;
 template <int MODE> constexpr int gemm_threads() { return 64 + 32 * kNumEpiWarps + (is_push<MODE>() ? 32 : 0); }
 
 constexpr int kStoreBoxBytes = 128 * 128;       // one TMA-store box: 128 rows x 128 bytes, 128B-swizzled
-constexpr int kStoreInflight = 2;               // TMA-store groups that may still be reading shared memory
+#ifndef FP8B_TMA_SLOTS
+#define FP8B_TMA_SLOTS 4                        // ring of 16 KB store boxes (kStTma); 2 leaves room for a sixth operand stage
+#endif
+constexpr int kStoreInflight = FP8B_TMA_SLOTS >= 4 ? 2 : 1;   // TMA-store groups that may still be reading shared memory
 // Warp roles.  The epilogue takes the LOW warp ids and the two single-thread roles the HIGH ones: the warp
 // scheduler favours higher warp ids among eligible warps, and the MMA issuer / TMA producer are latency-critical
 // (with the roles the other way round the epilogue's ALU stream delayed MMA issue: 14.2K vs 12.4K cycles per tile).
@@ -86,7 +89,7 @@ template <int BN, int CG, int MODE = kStDirect> struct GemmCfg {
     static constexpr int kBBytes = kBRows * kBK;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kSlotBytes = MODE == kStWide ? kBM * BN * 2 : kStoreBoxBytes;     // kStWide: 128 rows x BN 16-bit columns
-    static constexpr int kStoreSlots = MODE == kStWide ? (kSlotBytes <= 32768 ? 3 : 2) : 4; // ring of store boxes
+    static constexpr int kStoreSlots = MODE == kStWide ? (kSlotBytes <= 32768 ? 3 : 2) : FP8B_TMA_SLOTS; // ring of store boxes
     // epilogue staging: per epilogue warp 32 rows x 256 B, XOR-swizzled -- or the store ring
     static constexpr int kEpiStageBytes = is_push<MODE>() ? kStoreSlots * kSlotBytes : kNumEpiWarps * 8192;
     static constexpr int kStagesFit = (232448 - 1024 - 256 - kEpiStageBytes) / kStageBytes;
