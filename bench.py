@@ -1020,6 +1020,9 @@ def main():
         "roofline": {"bound": "tensor", "achieved": round(per_gpu, 1), "peak": round(fp8_peak, 1), "unit": "TFLOP/s",
                      "frac": round(per_gpu / fp8_peak, 4), "traffic": profile_traffic("gemm") if n_gpus == 1 else None,
                      "frac_of_nominal_4500": round(per_gpu / 4500.0, 4), "us_per_launch": round(kernel_us, 2),
+                     "frac_of_sustained_proxy": round(per_gpu / (2 * peaks["bf16_sustained"]), 4),
+                     "sustained_note": "MEASURED_PEAKS.json also has the bf16 cuBLAS rate of a seconds-long loop under the power cap; "
+                                       "`frac` uses the BURST figure although the timed region is milliseconds of back-to-back GEMMs",
                      "peak_source": f"{peaks['source']}: 2 x bf16 cuBLAS burst (MEASURED_PEAKS.json) as the dense-FP8 proxy",
                      "kernel": kernel_name, "flops_per_launch": C4_FLOPS // n_gpus},
         "e2e": e2e,
