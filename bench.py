@@ -808,7 +808,7 @@ def main():
         ms, launches_per_step, t0, t1 = time_graph(torch, step_single, steps, warmup)
         clocks = sampler.summary(t0, t1)
         kernel_us = ms / steps * 1e3 / SETS
-        kernel_name = "fp8b::fp8_gemm_tcgen05_kernel<256,2,0> (CTA pairs, 256x256 tiles)"
+        kernel_name = "fp8b::fp8_gemm_tcgen05_kernel<256,2,2> (CTA pairs, 256x256 tiles, TMA-store epilogue)"
     else:
         from fp8_sharded import ShardedScaledMM, shard_bounds
         lins = [ShardedScaledMM(w, inv_w, None) for (_, _, w, inv_w, _) in bufs]       # each keeps its own shard of W
