@@ -13,6 +13,7 @@ cap gemv fp8_gemv_kernel gemv
 cap gemv4 fp8_gemv_mma gemv4
 cap gemv1k4 fp8_gemv_kernel gemv1k4
 cap gemv_ring fp8_gemv_ring gemv_ring
+cap gemm_stg fp8_gemm_tcgen05 gemm_stg
 cap dequant fp8_to_wide dequant
 cap quant wide_to_fp8 quant
 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/plain_bench.log 2>&1 &&
