@@ -13,7 +13,9 @@ scales, bf16 out -- 309 237 645 312 flops per call.
     N > 1: STRONG scaling of the same problem: W is column-sharded over the ranks (ShardedScaledMM, mode "push"):
     ONE kernel per rank computes its (M, N/w) block on the tensor cores and pushes every finished box with TMA stores
     into the row-major (M, N) result of EVERY rank over NVLink; one symmetric-memory barrier closes the call.  A call
-    is complete when every rank holds the full result.
+    is complete when every rank holds the full result.  Timed like the N = 1 step, as CUDA graphs (two, replayed in
+    turn: consecutive calls alternate between the two result buffers); the same calls issued one by one from Python
+    are reported beside it (`sharded.plans.*.eager_us_per_call`).
   * value   = flops of all calls / time, CUDA events on the launching stream after W (>= 3) warm-up steps, barrier +
               synchronize on both sides, MAX over ranks.  Inputs resident in HBM.
   * e2e     = the same call through the public API with HOST (pinned) buffers inside the timed region:
@@ -832,6 +834,7 @@ def main():
             ref = o.scaled_mm(a0[:64].cpu().numpy(), w0.cpu().numpy(), inv_a0.cpu().numpy(), inv_w0.cpu().numpy(), None, None,
                               "bf16", accum="f32")
             oracle_err = float(o.rel_rmse(full0[:64].float().cpu().numpy(), ref))
+        GRAPH_PLANS = ("push", "peers", "multicast")
         plans = {"push_fused": ("push", "row_major"), "peer_store_fused": ("peers", "row_major"),
                  "multicast_fused": ("multicast", "row_major"), "allgather_row_major": ("allgather", "row_major"),
                  "allgather_rank_major": ("allgather", "rank_major")}
@@ -854,22 +857,65 @@ def main():
                 torch.cuda.synchronize()
                 dist.barrier()
                 torch.cuda.synchronize()
+                # the fused plans (one kernel + one barrier kernel per call) are timed like the N = 1 step: captured in
+                # CUDA graphs -- TWO of them, replayed alternately, because consecutive calls of a ShardedScaledMM use
+                # the two buffers of its symmetric pair in turn.  The NCCL plans allocate and call the collective from
+                # the host; they stay eager (their 190-300 us per call hide the host).
+                run_step, timing = fn, "eager"
+                n0_l = L.fp8b_launch_count()
+                graphs = []
+                if mode in GRAPH_PLANS:
+                    try:
+                        for _ in range(2):
+                            gr = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(gr):
+                                fn()
+                            graphs.append(gr)
+                    except Exception as e:         # capture refused (the same on every rank): time the eager loop
+                        entry["graph_capture_failed"] = repr(e)[:160]
+                        graphs = []
+                        torch.cuda.synchronize()
+                if graphs:
+                    launches_plan = int((L.fp8b_launch_count() - n0_l) // 2)
+                    turn = [0]
+
+                    def run_step():
+                        graphs[turn[0] & 1].replay()
+                        turn[0] += 1
+                    timing = "cuda_graph"
+                    for _ in range(max(warmup, 3)):
+                        run_step()
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    torch.cuda.synchronize()
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 n0_l = L.fp8b_launch_count()
                 tw0 = time.perf_counter()
                 e0.record()
                 for _ in range(steps):
-                    fn()
+                    run_step()
                 e1.record()
                 torch.cuda.synchronize()
                 tw1 = time.perf_counter()
                 dist.barrier()
                 t_ms = max_over_ranks(torch, dist, e0.elapsed_time(e1))
+                entry["timing"] = timing
                 entry["us_per_call"] = round(t_ms / steps * 1e3 / SETS, 2)
                 entry["tflops_total"] = round(C4_FLOPS / (entry["us_per_call"] * 1e-6) / 1e12, 1)
-                entry["launches_per_step"] = int((L.fp8b_launch_count() - n0_l) // steps)
+                entry["launches_per_step"] = launches_plan if timing == "cuda_graph" else int((L.fp8b_launch_count() - n0_l) // steps)
                 entry["_ms"], entry["_t0"], entry["_t1"] = t_ms, tw0, tw1
+                if graphs:                         # the same calls issued one by one from Python, for the record
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(steps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    entry["eager_us_per_call"] = round(max_over_ranks(torch, dist, e0.elapsed_time(e1)) / steps * 1e3 / SETS, 2)
             except Exception as e:                 # e.g. no NVLS multicast on this system: the plan did not run at all
                 entry["unavailable"] = repr(e)[:200]
                 entry["parity"] = None

@@ -249,7 +249,11 @@ class ShardedScaledMM:
     def forward_push(self, x_u8: torch.Tensor, scale_a: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
         """ONE kernel computes this rank's column block and pushes it, box by box, into the row-major (M,N) result
         of every rank (fp8b_scaled_mm_push: tcgen05 GEMM + TMA stores to local HBM and, over NVLink, to the peers'
-        symmetric buffers).  Same double-buffering and single closing barrier as forward_multicast."""
+        symmetric buffers).  Same double-buffering and single closing barrier as forward_multicast.
+
+        CUDA-graph capturable once the symmetric buffers exist (call it once eagerly first); capture TWO graphs and
+        replay them in turn if the double-buffering matters to the caller.  Do not let the last reference to a
+        symmetric buffer die inside a capture (freeing one is not a capturable operation)."""
         import fp8_mps_native
         M, K = x_u8.shape
         odt = out_dtype or torch.float32
@@ -261,7 +265,9 @@ class ShardedScaledMM:
         buf, hdl = pair[turn]
         self._symm = (key, pair, turn ^ 1)
         lib = fp8_mps_native._get_lib()
-        if self.fused_barrier and self._all_shards_nonempty():
+        if self.fused_barrier and self._all_shards_nonempty() and not torch.cuda.is_current_stream_capturing():
+            # (the epoch is a host-side count baked into the launch: a captured graph would replay a stale one, so under
+            # stream capture the call closes with the symmetric-memory barrier kernel below instead)
             # closing barrier fused into the exchange: the push kernel's last CTA stores this call's epoch into every
             # peer's flag word; fp8b_peer_wait (one warp, programmatic dependent launch, already resident) returns when
             # every peer's flag has arrived and this rank's own kernel has completed

@@ -97,6 +97,24 @@ def main():
                 torch.cuda.synchronize()
                 pu_ok = pu_ok and bool(torch.equal(ypu4, full))
                 lin.fused_barrier = world <= 2
+                # the call captured in CUDA graphs (one per buffer of the pair), replayed in turn as bench.py does; under
+                # capture the call must close with the barrier kernel (the fused barrier's epoch is a host-side count)
+                # (no name may drop its last reference to a symmetric buffer INSIDE a capture: freeing one is not a
+                # capturable operation -- hence the fresh list per capture and the explicit clean-up afterwards)
+                graphs, results = [], []
+                for _ in range(2):
+                    graphs.append(torch.cuda.CUDAGraph())
+                    with torch.cuda.graph(graphs[-1]):
+                        results.append(lin(Ad, sad, out_dtype=torch.bfloat16, mode="push"))
+                for i in range(6):
+                    results[i & 1].zero_()
+                    torch.cuda.synchronize()
+                    dist.barrier()                                                   # nobody pushes into a buffer still being cleared
+                    graphs[i & 1].replay()
+                    got = results[i & 1].clone()
+                    torch.cuda.synchronize()
+                    pu_ok = pu_ok and bool(torch.equal(got, full))
+                del graphs, results
                 pu_state = "ok" if pu_ok else "MISMATCH"
                 ok = ok and pu_ok
             except Exception as e:
