@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cstdio>
 #include <mutex>
+#include <type_traits>
+
 #include "fp8_mm.cuh"
 #include "fp8_async.cuh"
 
@@ -123,6 +125,7 @@ struct GemmParams {
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
     int raster_n;                            // tile order: 0 = M fastest (consecutive work items share a B tile), 1 = N fastest
+    int stage_tx;                            // bytes one CTA's two TMA loads deliver per stage (the A box is shorter when M < 128)
     int full_tiles;                          // work items [0, full_tiles) are BN-wide tiles ...
     int num_work;                            // ... items [full_tiles, num_work) are half-width tiles (last-wave split)
     Epi epi;
@@ -193,6 +196,16 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, naming the registers an earlier tcgen05.ld is filling as in/out operands: with two loads in flight
+// (software-pipelined epilogue) this is what keeps the compiler from scheduling a use of r[] above the wait.
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 // ---- cta_group::2 flavours (a CTA pair; rank 0 of the cluster is the leader) -------------------
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> even CTA
@@ -302,6 +315,53 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
     return c;
 }
 
+// The epilogue arithmetic of one 32-column chunk, in the reference's order (acc * scale_a * scale_b [+ bias] [* scale_result],
+// every step rounded to fp32), specialised on which optional terms exist so that the 32-element loop is branch-free:
+// with the three run-time tests inside the loop the chunk compiled to ~1000 SASS instructions and the epilogue of a
+// 128 x 256 accumulator took as long as its K = 3072 main loop (12 000 cycles, measured with the per-tile clock stamps).
+template <bool SBV, bool BIAS, bool SR>
+__device__ __forceinline__ void epi_math32(const uint32_t (&r)[32], float sa, float sb0, float sr, const float (&sbv)[32],
+                                           const float (&bv)[32], float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float x = __fmul_rn(__uint_as_float(r[j]), sa);
+        x = __fmul_rn(x, SBV ? sbv[j] : sb0);
+        if (BIAS) x = __fadd_rn(x, bv[j]);
+        if (SR) x = __fmul_rn(x, sr);
+        v[j] = x;
+    }
+}
+// NaN anywhere in the 32 accumulators of a lane?  (four independent add chains instead of one 32-long one)
+__device__ __forceinline__ bool any_nan32(const uint32_t (&r)[32]) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        s0 += __uint_as_float(r[j]); s1 += __uint_as_float(r[j + 1]);
+        s2 += __uint_as_float(r[j + 2]); s3 += __uint_as_float(r[j + 3]);
+    }
+    const float s = (s0 + s1) + (s2 + s3);
+    return s != s;
+}
+
+// Cold paths of the epilogue, out of line and working on local-memory copies, so that they cost the hot loop neither
+// instructions nor instruction-cache footprint (with the NaN fix-up inlined 32 times per chunk the 128 x 256 epilogue took
+// 8 100 cycles, without it 6 800; with the term dispatch hoisted out of the tile loop as well, 3 700).
+static __device__ __noinline__ void fix_nan_chunk(uint32_t* r, const uint8_t* a_row, const uint8_t* b_rows, int K, int n_left,
+                                                  int a_fmt, int b_fmt) {
+    for (int j = 0; j < 32 && j < n_left; ++j) {
+        const float a = __uint_as_float(r[j]);
+        if (a != a) r[j] = __float_as_uint(slow_dot_fmt(a_row, b_rows + (size_t)j * K, K, a_fmt, b_fmt));
+    }
+}
+static __device__ __noinline__ void load_col_params_edge(const Epi& e, int n0, int N, float* sbv, float* bv) {
+    for (int j = 0; j < 32; ++j) {
+        const int n = n0 + j;
+        const bool ok = n < N;
+        sbv[j] = (e.sb_stride && ok) ? e.sb[n] : 0.0f;
+        bv[j] = (e.bias && ok) ? epi_bias(e, n) : 0.0f;
+    }
+}
+
 // ------------------------------------------------------------------------------ kernel
 
 // Per-column epilogue parameters of one 32-column chunk, loaded while the TMEM load is in flight: one broadcast
@@ -391,10 +451,15 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
     const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+#ifdef FP8B_PROFILE
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[7] = clock64();       // kernel entry
+#endif
 
-    // push modes: let the kernel that follows on the stream (fp8b_peer_wait, launched with the PDL attribute) become
-    // resident now, so that its launch latency is behind it when the peers' completion flags arrive
-    if (is_push<MODE>()) pdl_launch_dependents();
+    // Programmatic dependent launch: let the kernel that follows on the stream become resident as soon as SMs free up
+    // (push modes: fp8b_peer_wait, so that its launch latency is behind it when the peers' completion flags arrive; a
+    // chain of GEMMs: the next one's barrier / TMEM / descriptor set-up).  It still waits -- griddepcontrol.wait below --
+    // for this grid to complete before it touches global memory.
+    pdl_launch_dependents();
 
     if (warp == kWarpTma && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -417,6 +482,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Everything above touched only this CTA's shared / tensor memory.  From here on the kernel reads A, B, the scales
+    // and the bias and writes C: the predecessor on the stream must have completed (no-op without the PDL attribute).
+    pdl_wait();
 
     const int num_tiles = p.num_work;
 
@@ -447,11 +515,11 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #endif
                         if (CG == 2) {
                             // both CTAs load their halves; all bytes are accounted on the leader's barrier
-                            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * CG);
+                            if (is_leader) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx * CG);
                             tma_load_2d_2sm(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
                             tma_load_2d_2sm(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
                         } else {
-                            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx);
                             tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
                             tma_load_2d(a_dst + Cfg::kABytes, &tmap_b, full_bar(stage), kb * kBK, n_idx);
                         }
@@ -553,6 +621,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (elected) bulk_wait_group_all();                   // all writes performed before the CTA retires
             __syncwarp();
+#ifdef FP8B_PROFILE
+            if (dbg && blockIdx.x == 0 && lane == 0) dbg[15] = clock64();         // stores complete
+#endif
         } else if constexpr (MODE == kStWide) {
             // one box per tile: 128 rows x the tile width, coordinates in 16-bit elements
             const bool elected = elect_one();
@@ -598,6 +669,144 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint32_t row_off = (uint32_t)row_in_tile * (kWide ? (uint32_t)(BN * 2) : 128u);
             uint32_t seq = 0;
             int acc = 0; uint32_t acc_phase = 0;
+            if constexpr (!kWide) {
+                // kStTma.  Software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is scaled, packed and
+                // staged (two register sets).  Which optional epilogue terms exist (KIND) is a compile-time constant of the
+                // whole tile loop -- one of eight copies runs -- and the cold paths (NaN fix-up, ragged column edge) are out
+                // of line, so the hot loop is short and contiguous: a 128 x 256 accumulator is drained in 3 700 cycles
+                // instead of 8 100-12 000.  That matters where the epilogue is exposed: the last tile of every CTA, i.e.
+                // all of a small problem.
+                auto run_tiles = [&](auto kind_c) {
+                    constexpr int KIND = decltype(kind_c)::value;
+                    constexpr bool SBV = (KIND & 1) != 0, BIAS = (KIND & 2) != 0, SR = (KIND & 4) != 0;
+                    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+                        const TileCoord tc = decode_tile(p, tile, BN);
+                        const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
+                        const int n_idx = tc.n0;
+                        const int m = m_idx + row_in_tile;
+                        const bool m_ok = m < p.M;
+                        const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
+                        const int nch = tc.width >> 5;                    // 32-column chunks in this tile (2..8), warp-uniform
+#ifdef FP8B_PROFILE
+                        const long long t_e0 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+#endif
+                        mbar_wait(tfull_bar(acc), acc_phase);
+                        tc_fence_after();
+#ifdef FP8B_PROFILE
+                        const long long t_e1 = (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) ? clock64() : 0;
+#endif
+                        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+                        auto release_acc = [&]() {                        // every tcgen05.ld of this accumulator has completed
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { if (CG == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+                        };
+                        auto chunk = [&](int c0, uint32_t (&r)[32]) {
+                            const int n0 = n_idx + c0;
+                            const int n_box = n_idx + (c0 & ~(cols_per_box - 1));
+                            if (n_box >= p.N) return;                     // whole box outside the matrix (warp-uniform): the store warp skips it too
+                            const bool box_first = (c0 & (cols_per_box - 1)) == 0;
+                            const bool box_last = ((c0 + 32) & (cols_per_box - 1)) == 0 || c0 + 32 == tc.width;
+                            const uint32_t slot = seq % Cfg::kStoreSlots;
+                            if (box_first) mbar_wait(sfree_bar(slot), ((seq / Cfg::kStoreSlots) & 1) ^ 1);
+                            if (n0 < p.N) {
+                                float sbv[32];
+                                float bv[32];
+                                if (SBV || BIAS) {
+                                    if ((n0 + 32 <= p.N) && p.col_vec_ok) {
+                                        load_col_params(e, n0, p.N, true, sbv, bv);
+                                    } else {                              // ragged edge / unaligned arrays (cold)
+                                        float t_sb[32], t_b[32];
+                                        load_col_params_edge(e, n0, p.N, t_sb, t_b);
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j) { sbv[j] = t_sb[j]; bv[j] = t_b[j]; }
+                                    }
+                                }
+                                // NaN-byte fix-up (cold): a NaN accumulator can only come from a 0x7F/0xFF operand byte
+                                if (__any_sync(0xFFFFFFFFu, m_ok && any_nan32(r))) {
+                                    uint32_t t[32];
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) t[j] = r[j];
+                                    if (m_ok) fix_nan_chunk(t, p.A + (size_t)m * p.K, p.B + (size_t)n0 * p.K, p.K, p.N - n0,
+                                                            (p.debug >> 8) & 1, (p.debug >> 9) & 1);
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) r[j] = t[j];
+                                }
+                                float v[32];
+                                epi_math32<SBV, BIAS, SR>(r, sa, sb0, sr, sbv, bv, v);
+                                const uint32_t dst = stage_base + slot * Cfg::kSlotBytes + row_off;
+                                const uint32_t sw = (uint32_t)(lane & 7);
+                                // first 16-byte piece of this chunk inside the box row
+                                const uint32_t piece0 = (uint32_t)(((c0 & (cols_per_box - 1)) * (is_f32 ? 4 : 2)) >> 4);
+                                if (is_f32) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j)
+                                        sts_v4(dst + (((piece0 + j) ^ sw) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                               __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+                                } else {
+                                    uint32_t pk[16];
+                                    if (e.out_dtype == FP8B_BF16) {
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j) {
+                                            __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                                            pk[j] = *reinterpret_cast<uint32_t*>(&b);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 16; ++j) {
+                                            __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                                        }
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        sts_v4(dst + (((piece0 + j) ^ sw) << 4), pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                                }
+                            }
+                            if (box_last) {
+                                fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA (async proxy)
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(sfull_bar(slot));
+                                ++seq;
+                            }
+                        };
+                        uint32_t ra[32], rb[32];
+                        __syncwarp();
+                        tmem_ld_x32(t_row, ra);
+#pragma unroll 1
+                        for (int ch = 0; ch < nch; ch += 2) {
+                            tmem_ld_wait_for(ra);
+                            __syncwarp();                   // lanes may have diverged in chunk() (row mask, NaN fix-up)
+                            if (ch + 1 < nch) tmem_ld_x32(t_row + (uint32_t)((ch + 1) * 32), rb); else release_acc();
+                            chunk(ch * 32, ra);
+                            if (ch + 1 < nch) {
+                                tmem_ld_wait_for(rb);
+                                __syncwarp();
+                                if (ch + 2 < nch) tmem_ld_x32(t_row + (uint32_t)((ch + 2) * 32), ra); else release_acc();
+                                chunk((ch + 1) * 32, rb);
+                            }
+                        }
+#ifdef FP8B_PROFILE
+                        if (dbg && blockIdx.x == 0 && warp == kWarpEpi0 && lane == 0) {
+                            const int ti = (tile - worker) / num_workers;
+                            if (ti < 64) { dbg[ti * 8 + 4] = t_e0; dbg[ti * 8 + 5] = t_e1; dbg[ti * 8 + 6] = clock64(); }
+                            dbg[23] = clock64();                                   // last epilogue end so far
+                        }
+#endif
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
+                };
+                switch ((e.sb_stride ? 1 : 0) | (e.bias ? 2 : 0) | (e.sr ? 4 : 0)) {          // grid-uniform
+                    case 0: run_tiles(std::integral_constant<int, 0>{}); break;
+                    case 1: run_tiles(std::integral_constant<int, 1>{}); break;
+                    case 2: run_tiles(std::integral_constant<int, 2>{}); break;
+                    case 3: run_tiles(std::integral_constant<int, 3>{}); break;
+                    case 4: run_tiles(std::integral_constant<int, 4>{}); break;
+                    case 5: run_tiles(std::integral_constant<int, 5>{}); break;
+                    case 6: run_tiles(std::integral_constant<int, 6>{}); break;
+                    default: run_tiles(std::integral_constant<int, 7>{}); break;
+                }
+            } else
             for (int tile = worker; tile < num_tiles; tile += num_workers) {
                 const TileCoord tc = decode_tile(p, tile, BN);
                 const int m_idx = tc.m_blk * kTileM + (int)cta_rank * kBM;
@@ -636,7 +845,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         float nan_probe = 0.0f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) nan_probe += __uint_as_float(r[j]);
-                        if (__any_sync(0xFFFFFFFFu, nan_probe != nan_probe)) {
+                        if (__any_sync(0xFFFFFFFFu, m_ok && nan_probe != nan_probe)) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const float a = __uint_as_float(r[j]);
@@ -754,7 +963,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 float nan_probe = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) nan_probe += __uint_as_float(r[j]);
-                if (__any_sync(0xFFFFFFFFu, nan_probe != nan_probe)) {
+                if (__any_sync(0xFFFFFFFFu, m_ok && nan_probe != nan_probe)) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float a = __uint_as_float(r[j]);
@@ -859,6 +1068,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tc_fence_before();
     if (CG == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while its peer still signals it
     else __syncthreads();
+#ifdef FP8B_PROFILE
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[31] = clock64();          // CTA end
+#endif
     if (warp == kWarpEpi0) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -1020,7 +1232,12 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     if (int rc = ensure_max_smem(fp8_gemm_tcgen05_kernel<BN, CG, MODE>, Cfg::kSmemBytes, attr_done)) return rc;
 
     CUtensorMap tmap_a, tmap_b;
-    if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, kBM)) return FP8B_ERR_CUDA;
+    // A problem shorter than one tile loads only its own rows (rounded up to the 8-row swizzle atom): a 128-row box over
+    // a matrix of <= 40 rows was measured to run the main loop at HALF speed (M = 32: 16.2 us, M = 48: 11.8 us for
+    // K = 3072, N = 12288).  The rows of the stage beyond the box keep stale shared memory; they only feed accumulator
+    // rows >= M, which are never stored (and are masked out of the NaN probe).
+    const int a_box_rows = a.M < kBM ? ((a.M + 7) / 8) * 8 : kBM;
+    if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, a_box_rows)) return FP8B_ERR_CUDA;
     if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, Cfg::kBRows)) return FP8B_ERR_CUDA;
 
     const size_t esz = dtype_size(a.out_dtype);
@@ -1060,6 +1277,7 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     p.debug = (a.a_fmt ? 0x100 : 0) | (a.b_fmt ? 0x200 : 0);
     p.store_mc = a.store_mc;
     p.aux = nullptr;
+    p.stage_tx = a_box_rows * kBK + Cfg::kBBytes;
     typename StoreMapsOf<MODE>::type smaps;
     if constexpr (MODE == kStPeers) {        // store_mc = 2 | world << 8; a.ws = device table of world byte deltas
         p.aux = static_cast<long long*>(a.ws);
@@ -1087,7 +1305,9 @@ static int launch_tcgen05_cfg(const MMArgs& a)
         fill_signal(smaps, a);
     } else {
         smaps.unused = 0;
+    }
 #ifdef FP8B_PROFILE
+    if constexpr (MODE != kStPeers) {
         p.debug |= tune_int("FP8B_GEMM_DEBUG", 0) & 0xFF;
         if (p.debug & 16) {                  // profiling only: allocates and synchronises
             static long long* dbuf = nullptr;
@@ -1095,8 +1315,8 @@ static int launch_tcgen05_cfg(const MMArgs& a)
             cudaMemset(dbuf, 0, 64 * 8 * sizeof(long long));
             p.aux = dbuf;
         }
-#endif
     }
+#endif
     // multimem.st / peer stores have no sub-word form: both modes need every chunk on the 16-byte path
     if (!is_push<MODE>() && a.store_mc && !(p.vec_store_ok && p.col_vec_ok && a.N % 32 == 0)) return FP8B_ERR_UNSUPPORTED;
 
@@ -1109,24 +1329,31 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     cfg.blockDim = dim3(gemm_threads<MODE>(), 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = a.st;
-    cudaLaunchAttribute attr[2];
+    cudaLaunchAttribute attr[3];
     int nattr = 0;
     if (CG > 1) {
         attr[nattr].id = cudaLaunchAttributeClusterDimension;
         attr[nattr].val.clusterDim.x = CG; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
         ++nattr;
     }
-    // (Programmatic dependent launch was measured here too -- prologue overlapped with the predecessor's tail -- and
-    // changed nothing: 104.17 vs 104.12 us back to back.  The kernel is power-limited, idle gaps only buy clock.)
+    // Programmatic dependent launch (FP8B_OPT_PDL): the prologue overlaps the predecessor's tail.  Worth nothing on C4
+    // (104.17 vs 104.12 us back to back: power-limited, idle gaps only buy clock) but a fixed ~2 us on small problems.
+    if (g_opt_pdl.load(std::memory_order_relaxed)) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_tcgen05_kernel<BN, CG, MODE>, tmap_a, tmap_b, smaps, p);
     if (e != cudaSuccess) return cuda_fail(e);
 #ifdef FP8B_PROFILE
-    if (MODE == kStDirect && p.aux) {
+    if (MODE != kStPeers && p.aux) {
         long long h[64 * 8];
         cudaDeviceSynchronize();
         cudaMemcpy(h, p.aux, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("CTA 0: kernel entry -> first MMA wait %lld cycles; last epilogue end -> stores complete %lld; -> CTA end %lld\n",
+               h[0] - h[7], h[15] ? h[15] - h[23] : 0, h[31] - (h[15] ? h[15] : h[23]));
         printf("tile | mma: wait_tempty  issue+run (of which waiting for TMA) | epi: wait_tfull  drain+store | epi_end - mma_end\n");
         for (int t = 0; t < 64 && h[t * 8 + 2]; ++t)
             printf("%4d | %8lld %8lld (%8lld) | %8lld %8lld | %8lld   (mma start %lld)\n", t, h[t * 8 + 1] - h[t * 8 + 0],

@@ -2,6 +2,7 @@
 """Launch one hot-path kernel a few times -- the short command ncu wraps (profiles/README.md).
 
     python profiles/run_kernels.py gemm|gemm_stg|gemm_push2|gemv|gemv4|gemv1k4|gemv_ring|quant|dequant [reps]
+    python profiles/run_kernels.py mm:M,K,N[:cfg] [reps]        # any fp8b_scaled_mm shape (AUTO dispatch), optional tile cfg
 """
 import ctypes
 import os
@@ -54,6 +55,18 @@ def main():
         for i in range(reps):
             rc = L.fp8b_scaled_mm(P(A), P(Bs[i % 4]), P(C), dt_code(torch.bfloat16), M, N, K, N, P(one), 1, P(one), 1,
                                   None, 0, None, None, 0, algo, st)
+            assert rc == 0, rc
+    elif which.startswith("mm:"):
+        parts = which.split(":")
+        M, K, N = (int(v) for v in parts[1].split(","))
+        if len(parts) > 2:
+            L.fp8b_set_option(16, int(parts[2]))
+        A = rand_u8(M, K)
+        Bs = [rand_u8(N, K) for _ in range(4)]
+        C = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        for i in range(reps):
+            rc = L.fp8b_scaled_mm(P(A), P(Bs[i % 4]), P(C), dt_code(torch.bfloat16), M, N, K, N, P(one), 1, P(one), 1,
+                                  None, 0, None, None, 0, 0, st)
             assert rc == 0, rc
     elif which in ("quant", "dequant"):
         n = 21504 * 3072 * (8 if os.environ.get("FP8B_PROFILE_BIG") else 1)      # the largest FLUX tensor of C5 (198 MB of traffic)

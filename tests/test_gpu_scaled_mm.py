@@ -503,6 +503,40 @@ def test_pdl_chain_sees_fresh_activations(M):
         assert torch.equal(y, ref), f"iteration {it}: chained result differs from the unchained one"
 
 
+@pytest.mark.parametrize("shape", [(256, 512, 384), (300, 1024, 1000)])
+def test_pdl_chain_gemm_sees_fresh_operands(shape):
+    """The tcgen05 GEMM is launched with programmatic dependent launch too: its prologue runs while the predecessor
+    drains, and nothing global may be read before griddepcontrol.wait.  Both operands are re-quantised on the device
+    (kernels that trigger their dependents early) into the SAME buffers right before every GEMM of a chain, and a GEMM
+    follows a GEMM whose output buffer is reused: a stale read or an early write changes a result."""
+    import fp8_mps_native
+    M, K, N = shape
+    g = torch.Generator(device=DEV).manual_seed(11)
+    xs = [torch.randn(M, K, device=DEV, generator=g) * (1.0 + i) for i in range(12)]
+    ws = [torch.randn(N, K, device=DEV, generator=g) * (0.5 + 0.1 * i) for i in range(12)]
+    refs = []
+    for x, w in zip(xs, ws):                                      # unchained: a synchronize after every step
+        qa, ia = fp8_mps_native.fp8_quantize(x)
+        qw, iw = fp8_mps_native.fp8_quantize(w)
+        torch.cuda.synchronize()
+        refs.append(fp8_mps_native.fp8_scaled_mm_fused(qa, qw, ia, iw, None, None, torch.bfloat16, algo=2).clone())
+        torch.cuda.synchronize()
+    qa_buf = torch.empty(M, K, dtype=torch.uint8, device=DEV)
+    qw_buf = torch.empty(N, K, dtype=torch.uint8, device=DEV)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    outs = []
+    for x, w in zip(xs, ws):                                      # chained: no host synchronisation at all
+        qa, ia = fp8_mps_native.fp8_quantize(x)
+        qw, iw = fp8_mps_native.fp8_quantize(w)
+        qa_buf.copy_(qa); qw_buf.copy_(qw)
+        fp8_mps_native.fp8_scaled_mm_fused(qa_buf, qw_buf, ia, iw, None, None, torch.bfloat16, algo=2, out=out)
+        fp8_mps_native.fp8_scaled_mm_fused(qa_buf, qw_buf, ia, iw, None, None, torch.bfloat16, algo=2, out=out)   # GEMM behind a GEMM
+        outs.append(out.clone())
+    torch.cuda.synchronize()
+    for i, (y, ref) in enumerate(zip(outs, refs)):
+        assert torch.equal(y, ref), f"step {i}: chained result differs from the unchained one"
+
+
 @pytest.mark.parametrize("M", [1, 3])
 def test_static_weights_option_sees_fresh_activations(M):
     """Same hazard through FP8B_OPT_STATIC_WEIGHTS: only B may be read before the wait."""
