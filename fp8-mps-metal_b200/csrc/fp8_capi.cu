@@ -47,7 +47,7 @@ std::atomic<int> g_tune[kTuneCount];
 namespace {
 const char* const kTuneEnv[kTuneCount] = {"FP8B_GEMM_CFG", "FP8B_GEMV_IMPL", "FP8B_DYNAMIC_PLAN", "FP8B_CAST_SHAPE",
                                           "FP8B_GEMM_STORE", "FP8B_GEMV_UNROLL", "FP8B_GEMV_BATCH", "FP8B_AMAX_CAP",
-                                          "FP8B_GEMM_RASTER"};
+                                          "FP8B_GEMM_RASTER", "FP8B_GEMM_SPLITK"};
 struct TuneInit {
     TuneInit() { for (int k = 0; k < kTuneCount; ++k) g_tune[k].store(env_int(kTuneEnv[k], -1)); }
 } g_tune_init;

@@ -30,7 +30,7 @@ const DeviceInfo& device_info();
 // variable of the same name (FP8B_GEMM_CFG, ...) read ONCE when the library is loaded -- never per call -- and none
 // of them can change a result.  -1 = unset (use the built-in rule).
 enum TuneKnob { kTuneGemmCfg = 0, kTuneGemvImpl, kTuneDynamicPlan, kTuneCastShape, kTuneGemmStore, kTuneGemvUnroll,
-                kTuneGemvBatch, kTuneAmaxCap, kTuneGemmRaster, kTuneCount };
+                kTuneGemvBatch, kTuneAmaxCap, kTuneGemmRaster, kTuneGemmSplitK, kTuneCount };
 extern std::atomic<int> g_tune[kTuneCount];
 inline int tune(TuneKnob k, int dflt) { const int v = g_tune[k].load(std::memory_order_relaxed); return v < 0 ? dflt : v; }
 #ifdef FP8B_PROFILE

@@ -219,6 +219,12 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution barrier only: no memory ordering.  For the end of a kernel, where the release flavour would first wait for
+// every global store of the epilogue to be acknowledged (measured: 2 000-4 000 cycles in the split-K kernel).
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 // TMA load issued by either CTA of the pair; the bytes are accounted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -1095,6 +1101,298 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 }
 
+// ------------------------------------------------------------------------------ split-K kernel (few tiles, long K)
+//
+// A problem with fewer 128 x 128 tiles than SMs leaves most of the GPU idle and every busy SM walks the whole of K alone
+// (M = 32, K = N = 3072: 24 CTAs, 6 100 cycles of MMAs each).  Here a thread-block CLUSTER of S CTAs shares one tile: CTA r
+// accumulates k-blocks [r, r+1) * KB / S into its own TMEM accumulator, then the cluster reduce-scatters over distributed
+// shared memory -- CTA r sends column slice j of its partial tile to CTA j (st.shared::cluster) and receives slice r of
+// every partial -- and each CTA sums its slice in rank order (deterministic), applies the epilogue and stores it.  The
+// reduction costs 64 KB of DSMEM traffic per CTA and spreads the epilogue over the S CTAs as well.
+//   warps 0..3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer; one tile per cluster.
+constexpr int kSkStages = 5;
+constexpr int kSkStageBytes = 2 * kBM * kBK;                     // A 128 x 128 B + B 128 x 128 B
+constexpr int kSkRecvBytes = kBM * 128 * 4;                      // S slots x 128 rows x (128 / S) fp32 columns = 64 KB
+constexpr int kSkBarBytes = 128;
+constexpr int kSkSmemBytes = kSkStages * kSkStageBytes + kSkRecvBytes + kSkBarBytes + 1024;
+constexpr int kSkThreads = 192;
+
+struct SplitKParams {
+    const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
+    int M, N, K;
+    int num_n_blocks, num_k_blocks;
+    int stage_tx;                            // bytes the two TMA loads of a stage deliver
+    uint32_t idesc;                          // instruction descriptor incl. operand formats
+    int a_fmt, b_fmt;
+    Epi epi;
+    int vec_store_ok;                        // C base and ldc allow 16-byte stores
+    int col_vec_ok;                          // scale_b / bias bases allow 16-byte broadcast loads
+    long long* dbg;                          // FP8B_PROFILE builds: clock stamps of CTA 0 (else null)
+};
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+// shared memory of this CTA -> shared memory of a CTA of the cluster, completion counted in bytes on THAT CTA's mbarrier
+__device__ __forceinline__ void bulk_copy_to_cta(uint32_t dst_cluster_addr, uint32_t src_local_addr, uint32_t bytes,
+                                                 uint32_t cluster_bar_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_cluster_addr), "r"(src_local_addr), "r"(bytes), "r"(cluster_bar_addr) : "memory");
+}
+// ragged column edge / unaligned output: element-wise, bounds-checked (cold)
+static __device__ __noinline__ void store_row_edge(const Epi& e, int m, int n0, int N, const float* v) {
+    for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) epi_store(e, m, n0 + j, v[j]);
+}
+template <int S>
+__global__ void __launch_bounds__(kSkThreads, 1)
+fp8_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const SplitKParams p)
+{
+    constexpr int kSlice = 128 / S;                  // output columns this CTA finishes
+    constexpr int kPieces = kSlice / 4;              // 16-byte pieces per row of a receive slot (>= 8)
+    constexpr int kSlotBytes = kBM * kSlice * 4;
+    static_assert(S == 2 || S == 4, "slices must be whole 32-column TMEM chunks");
+    extern __shared__ uint8_t gemm_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t recv_base = smem_base + kSkStages * kSkStageBytes;
+    const uint32_t bar_base = recv_base + kSkRecvBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kSkStages + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * kSkStages);
+    auto recv_bar = [&](int q) { return bar_base + 8u * (2 * kSkStages + 1 + q); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSkStages * kSkStageBytes + kSkRecvBytes + 8 * (2 * kSkStages + 5));
+
+    const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int tile = (int)(blockIdx.x / S);
+    const int n_blk = tile % p.num_n_blocks, m_blk = tile / p.num_n_blocks;
+    const int m_idx = m_blk * kBM, n_idx = n_blk * 128;
+    const int kb0 = (int)(((long long)p.num_k_blocks * rank) / S), kb1 = (int)(((long long)p.num_k_blocks * (rank + 1)) / S);
+
+    pdl_launch_dependents();
+#ifdef FP8B_PROFILE
+    const bool stamp = p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) p.dbg[0] = clock64();
+#endif
+    if (warp == 4 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+    if (warp == 5 && lane == 0) {
+        for (int s = 0; s < kSkStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        for (int q = 0; q < 4; ++q) mbar_init(recv_bar(q), 1);
+        fence_mbar_init();
+        // each receive barrier completes when warp q's block of every CTA of the cluster (S x 32 rows x kSlice fp32) has landed
+        for (int q = 0; q < 4; ++q) mbar_arrive_expect_tx(recv_bar(q), (uint32_t)(S * 32 * kSlice * 4));
+        fence_proxy_async_smem();
+    }
+    if (warp == 0) { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 128); tmem_relinquish(); }
+    tc_fence_before();
+    cluster_sync_all();                              // the peers' barriers exist before anybody arrives on them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // the predecessor on the stream has completed: global memory may be touched
+#ifdef FP8B_PROFILE
+    if (stamp) p.dbg[1] = clock64();
+#endif
+
+    if (warp == 4) {
+        const bool elected = elect_one();
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (elected) {
+                const uint32_t dst = smem_base + stage * kSkStageBytes;
+                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.stage_tx);
+                tma_load_2d(dst, &tmap_a, full_bar(stage), kb * kBK, m_idx);
+                tma_load_2d(dst + kBM * kBK, &tmap_b, full_bar(stage), kb * kBK, n_idx);
+            }
+            __syncwarp();
+            if (++stage == kSkStages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 5) {
+        const bool elected = elect_one();
+        const uint64_t desc_a0 = make_smem_desc(smem_base);
+        const uint64_t desc_b0 = make_smem_desc(smem_base + kBM * kBK);
+        constexpr uint64_t kDescStage = (uint64_t)(kSkStageBytes >> 4);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            if (elected) {
+                const uint64_t adesc = desc_a0 + kDescStage * (uint64_t)stage, bdesc = desc_b0 + kDescStage * (uint64_t)stage;
+#pragma unroll
+                for (int k = 0; k < kBK / kUmmaK; ++k)
+                    umma_f8(tmem_base, adesc + 2 * k, bdesc + 2 * k, p.idesc, (uint32_t)((kb != kb0) | (k != 0)));
+                umma_commit(empty_bar(stage));
+            }
+            __syncwarp();
+            if (++stage == kSkStages) { stage = 0; phase ^= 1; }
+        }
+        if (elected) umma_commit(tfull_bar);
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps: reduce-scatter over DSMEM, then finish this CTA's column slice =====================
+        // Scatter: the partial tile is staged in the (now idle) operand ring as [destination CTA][warp][32 rows][kSlice fp32]
+        // and every (warp, destination) block -- 32 * kSlice * 4 contiguous bytes -- travels as ONE bulk copy, shared memory
+        // to the peer's shared memory, completing on the PEER's mbarrier.  (Per-lane st.shared::cluster of 16 bytes was
+        // measured at 2 400 cycles per 32-column chunk: every lane writes a different row, nothing coalesces.)
+        const int q = warp;                           // TMEM lane quarter
+        const int row = q * 32 + lane;
+        const int m = m_idx + row;
+        const bool m_ok = m < p.M;
+        const Epi& e = p.epi;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        constexpr uint32_t kBlockBytes = 32u * kSlice * 4u;                   // one warp's rows of one slice
+        const uint32_t lane_off = (uint32_t)lane * (uint32_t)(kSlice * 4);
+        mbar_wait(tfull_bar, 0);                      // every MMA of this CTA has retired: TMEM complete, operand ring idle
+        tc_fence_after();
+#ifdef FP8B_PROFILE
+        if (stamp) p.dbg[2] = clock64();
+#endif
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        // (destinations in the order rank+1, rank+2, ..., rank: every CTA of the cluster receives its blocks at about the
+        // same time instead of CTA 0 first and CTA S-1 a whole scatter later)
+#pragma unroll 1
+        for (int i = 0; i < 128; i += 32) {
+            const int c0 = (i + ((int)rank + 1) * kSlice) & 127;
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_x32(t_row + (uint32_t)c0, r);
+            tmem_ld_wait_for(r);
+            const uint32_t dst_cta = (uint32_t)(c0 / kSlice);
+            const uint32_t blk = smem_base + (dst_cta * 4u + (uint32_t)q) * kBlockBytes;      // send[dst][q]
+            const uint32_t piece0 = (uint32_t)((c0 % kSlice) >> 2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                sts_v4(blk + lane_off + (((piece0 + j) ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            if ((c0 + 32) % kSlice == 0) {            // the block for dst_cta is complete: ship it
+                fence_proxy_async_smem();             // generic-proxy writes -> visible to the bulk copy (async proxy)
+                __syncwarp();
+                if (lane == 0)
+                    bulk_copy_to_cta(map_to_cta(recv_base + (rank * 4u + (uint32_t)q) * kBlockBytes, dst_cta), blk, kBlockBytes,
+                                     map_to_cta(recv_bar(q), dst_cta));
+            }
+        }
+#ifdef FP8B_PROFILE
+        if (stamp) p.dbg[3] = clock64();
+#endif
+        // gather: block [s][q] of every CTA s of the cluster (this one included) has landed in recv[s][q]
+        mbar_wait(recv_bar(q), 0);
+#ifdef FP8B_PROFILE
+        if (stamp) p.dbg[4] = clock64();
+#endif
+        const float sa = e.sa[(size_t)(m_ok ? m : 0) * e.sa_stride];
+        const float sr = e.sr ? *e.sr : 1.0f;
+        const float sb0 = e.sb[0];
+        const bool is_f32 = e.out_dtype == FP8B_F32;
+        const int esz = is_f32 ? 4 : 2;
+        const int kind = (e.sb_stride ? 1 : 0) | (e.bias ? 2 : 0) | (e.sr ? 4 : 0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < kSlice; c0 += 32) {
+            const int n0 = n_idx + (int)rank * kSlice + c0;
+            if (n0 >= p.N) break;                     // warp-uniform
+            uint32_t acc[32];
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) {          // rank order: the sum is the same on every run
+                const uint32_t src = recv_base + ((uint32_t)s2 * 4u + (uint32_t)q) * kBlockBytes + lane_off;
+                const uint32_t piece0 = (uint32_t)(c0 >> 2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t a0, a1, a2, a3;
+                    lds_v4(src + (((piece0 + j) ^ sw) << 4), a0, a1, a2, a3);
+                    if (s2 == 0) {
+                        acc[4 * j] = a0; acc[4 * j + 1] = a1; acc[4 * j + 2] = a2; acc[4 * j + 3] = a3;
+                    } else {
+                        acc[4 * j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[4 * j]), __uint_as_float(a0)));
+                        acc[4 * j + 1] = __float_as_uint(__fadd_rn(__uint_as_float(acc[4 * j + 1]), __uint_as_float(a1)));
+                        acc[4 * j + 2] = __float_as_uint(__fadd_rn(__uint_as_float(acc[4 * j + 2]), __uint_as_float(a2)));
+                        acc[4 * j + 3] = __float_as_uint(__fadd_rn(__uint_as_float(acc[4 * j + 3]), __uint_as_float(a3)));
+                    }
+                }
+            }
+            const bool full = (n0 + 32 <= p.N);
+            float sbv[32];
+            float bv[32];
+            if (kind & 3) {
+                if (full && p.col_vec_ok) {
+                    load_col_params(e, n0, p.N, true, sbv, bv);
+                } else {                              // ragged edge / unaligned arrays (cold)
+                    float t_sb[32], t_b[32];
+                    load_col_params_edge(e, n0, p.N, t_sb, t_b);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { sbv[j] = t_sb[j]; bv[j] = t_b[j]; }
+                }
+            }
+            // NaN-byte fix-up (cold): recompute the element over the whole of K with the reference's masked decode
+            if (__any_sync(0xFFFFFFFFu, m_ok && any_nan32(acc))) {
+                uint32_t t[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = acc[j];
+                if (m_ok) fix_nan_chunk(t, p.A + (size_t)m * p.K, p.B + (size_t)n0 * p.K, p.K, p.N - n0, p.a_fmt, p.b_fmt);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = t[j];
+            }
+            float v[32];
+            switch (kind) {                           // grid-uniform
+                case 0: epi_math32<false, false, false>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 1: epi_math32<true, false, false>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 2: epi_math32<false, true, false>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 3: epi_math32<true, true, false>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 4: epi_math32<false, false, true>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 5: epi_math32<true, false, true>(acc, sa, sb0, sr, sbv, bv, v); break;
+                case 6: epi_math32<false, true, true>(acc, sa, sb0, sr, sbv, bv, v); break;
+                default: epi_math32<true, true, true>(acc, sa, sb0, sr, sbv, bv, v); break;
+            }
+            if (!m_ok) continue;
+            if (full && p.vec_store_ok) {
+                uint8_t* dst = reinterpret_cast<uint8_t*>(e.C) + ((size_t)m * e.ldc + n0) * esz;
+                if (is_f32) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        stg_v4(dst + 16 * j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                               __float_as_uint(v[4 * j + 3]), 0);
+                } else {
+                    uint32_t pk[16];
+                    if (e.out_dtype == FP8B_BF16) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&b);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                            pk[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) stg_v4(dst + 16 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3], 0);
+                }
+            } else {
+                float t[32];                          // (a local copy: v itself stays in registers on the hot path)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = v[j];
+                store_row_edge(e, m, n0, p.N, t);
+            }
+        }
+    }
+    // Nobody writes into this CTA's shared memory any more: its own gather has seen every peer's arrival.  A CTA's
+    // own remote stores and arrives precede its gather wait only in program order, so all CTAs leave together.
+#ifdef FP8B_PROFILE
+    if (stamp) p.dbg[5] = clock64();
+#endif
+    tc_fence_before();
+    cluster_sync_relaxed();               // (data moved under mbarriers; this only keeps every CTA's shared memory alive)
+#ifdef FP8B_PROFILE
+    if (stamp) p.dbg[6] = clock64();
+#endif
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
 // Receive side of the fused closing barrier: returns (completes) when every peer's flag has reached `epoch`, i.e. every
 // peer's push kernel has finished writing into this rank's buffer -- and, through griddepcontrol.wait, when this rank's own
 // push kernel (its predecessor on the stream) has completed.  Launched with the PDL attribute: it is resident and
@@ -1364,6 +1662,88 @@ static int launch_tcgen05_cfg(const MMArgs& a)
     return after_launch();
 }
 
+// Split-K plan (fp8_gemm_splitk_kernel): clusters of S CTAs, one 128 x 128 tile each.
+template <int S>
+static int launch_splitk(const MMArgs& a)
+{
+    static std::atomic<int> attr_done[64];
+    if (int rc = ensure_max_smem(fp8_gemm_splitk_kernel<S>, kSkSmemBytes, attr_done)) return rc;
+    const int a_box_rows = a.M < kBM ? ((a.M + 7) / 8) * 8 : kBM;      // see launch_tcgen05_cfg
+    CUtensorMap tmap_a, tmap_b;
+    if (!encode_operand_map(&tmap_a, a.A, a.M, a.K, a_box_rows)) return FP8B_ERR_CUDA;
+    if (!encode_operand_map(&tmap_b, a.B, a.N, a.K, 128)) return FP8B_ERR_CUDA;
+    const size_t esz = dtype_size(a.out_dtype);
+    SplitKParams p;
+    p.A = a.A; p.B = a.B; p.M = a.M; p.N = a.N; p.K = a.K;
+    p.num_n_blocks = (a.N + 127) / 128;
+    p.num_k_blocks = (a.K + kBK - 1) / kBK;
+    p.stage_tx = a_box_rows * kBK + 128 * kBK;
+    p.idesc = make_idesc(kBM, 128) | ((uint32_t)(a.a_fmt ? 1 : 0) << 7) | ((uint32_t)(a.b_fmt ? 1 : 0) << 10);
+    p.a_fmt = a.a_fmt; p.b_fmt = a.b_fmt;
+    p.epi = make_epi(a);
+    p.vec_store_ok = aligned(a.C, 16) && ((a.ldc * esz) % 16 == 0);
+    p.col_vec_ok = (a.sb_len == 1 || aligned(a.sb, 16)) && (!a.bias || aligned(a.bias, 16));
+    p.dbg = nullptr;
+#ifdef FP8B_PROFILE
+    if (tune_int("FP8B_GEMM_DEBUG", 0) & 16) {     // profiling only: allocates and synchronises
+        static long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 8 * sizeof(long long));
+        cudaMemset(dbuf, 0, 8 * sizeof(long long));
+        p.dbg = dbuf;
+    }
+#endif
+    const long tiles = (long)((a.M + kBM - 1) / kBM) * p.num_n_blocks;
+    if (p.num_k_blocks < S || tiles * S > 65535L * 16) return FP8B_ERR_UNSUPPORTED;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * S), 1, 1);
+    cfg.blockDim = dim3(kSkThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSkSmemBytes;
+    cfg.stream = a.st;
+    cudaLaunchAttribute attr[2];
+    int nattr = 0;
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = S; attr[nattr].val.clusterDim.y = 1; attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+    if (g_opt_pdl.load(std::memory_order_relaxed)) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = nattr;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fp8_gemm_splitk_kernel<S>, tmap_a, tmap_b, p);
+    if (e != cudaSuccess) return cuda_fail(e);
+#ifdef FP8B_PROFILE
+    if (p.dbg) {
+        long long h[8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, p.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("split-K x%d, CTA 0 thread 0 (cycles): prologue %lld | main loop %lld | scatter %lld | wait for peers %lld | "
+               "reduce+store %lld | final cluster sync %lld\n", S, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4],
+               h[6] - h[5]);
+    }
+#endif
+    return after_launch();
+}
+
+// How many CTAs should share one tile (0 = the ordinary plans).  Split K when all clusters fit on the GPU at once and K
+// is long enough to pay for the reduction (~2 000 cycles of scatter / wait / gather).  Calibrated on the sweep in
+// profiles/r2_splitk_calibration.log (us, no split / 2 / 4): M=32 K=N=3072 8.9 / 8.1 / 7.1; M=128 K=8192 N=2048 18.0 / 12.9 /
+// 9.6; M=32 K=14336 N=4096 28.3 / 19.8 / 16.0; M=256 K=N=3072 9.7 / 8.8 / 13.7 (192 CTAs: two waves); K=1024: never a gain.
+// FP8B_OPT_TUNE_GEMM_SPLITK: 1 = never, 2 / 4 = force.
+static int pick_split_k(const MMArgs& a)
+{
+    const int forced = tune(kTuneGemmSplitK, 0);
+    if (forced == 1) return 0;
+    const int kb = (a.K + kBK - 1) / kBK;
+    if (forced == 2 || forced == 4) return kb >= forced ? forced : 0;
+    const long tiles = (long)((a.M + kBM - 1) / kBM) * ((a.N + 127) / 128);
+    const int sms = device_info().sm_count;
+    if (tiles * 4 <= sms && kb >= 16) return 4;
+    if (tiles * 2 <= sms && kb >= 24) return 2;
+    return 0;
+}
+
 constexpr bool kPushWideDefault = false;   // push to peers: one linear box per tile instead of 128-byte-wide boxes (measured choice)
 constexpr int kDefaultGemmStore = 2;      // epilogue of plain fp8b_scaled_mm calls: 1 = st.global from the epilogue warps, 2 = TMA
                                           // store (C4: 109.7 vs 112.0 us in the same bench run; falls back to 1 when C is not TMA-storable)
@@ -1404,6 +1784,11 @@ int launch_gemm_tcgen05(const MMArgs& a)
     const int forced = tune(kTuneGemmCfg, 0);
     int cfg = forced ? forced : pick_tile_cfg(a);
     const int mode = a.store_mc & 0xFF;
+    if (mode == 0 && !forced) {               // plain call: few tiles and a long K -> several CTAs per tile
+        const int split = pick_split_k(a);
+        if (split == 4) return launch_splitk<4>(a);
+        if (split == 2) return launch_splitk<2>(a);
+    }
     // Pushing to peers the kernel is bound by NVLink, not by the tensor pipe, and the link idles until the first tiles
     // are complete: narrower tiles (256 x 128) halve that ramp at no cost in exchange time (measured at w = 2:
     // 103.4 us against 106.4 us with 256 x 256 tiles; profiles/r2_scaling.md).

@@ -94,6 +94,10 @@ FP8B_API uint64_t fp8b_launch_count(void);
  *                              GEMM_STORE    tcgen05 epilogue: 1 = st.global from the epilogue warps, 2 = TMA store
  *                              GEMV_UNROLL / GEMV_BATCH / AMAX_CAP   load batching of the GEMV kernels / amax grid cap
  *                              GEMM_RASTER   tcgen05 tile order: 1 = M fastest, 2 = N fastest (whole output rows complete together)
+ *                              GEMM_SPLITK   split-K plan for problems with few tiles: 1 = never, 2 / 4 = that many CTAs per tile.
+ *                                            (The one knob that is not bit-neutral: partial sums over K ranges are added in
+ *                                            rank order, so results are deterministic but rounded differently from the
+ *                                            one-CTA-per-tile plans; both are within the stated tolerances of the oracle.)
  */
 typedef enum fp8b_option {
     FP8B_OPT_PDL = 0,
@@ -106,7 +110,8 @@ typedef enum fp8b_option {
     FP8B_OPT_TUNE_GEMV_UNROLL = 21,
     FP8B_OPT_TUNE_GEMV_BATCH = 22,
     FP8B_OPT_TUNE_AMAX_CAP = 23,
-    FP8B_OPT_TUNE_GEMM_RASTER = 24
+    FP8B_OPT_TUNE_GEMM_RASTER = 24,
+    FP8B_OPT_TUNE_GEMM_SPLITK = 25
 } fp8b_option;
 FP8B_API int fp8b_set_option(int option, int value);
 FP8B_API int fp8b_get_option(int option);

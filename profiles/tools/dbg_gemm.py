@@ -17,5 +17,5 @@ C=torch.empty(M,N,dtype=torch.bfloat16,device=dev); one=torch.full((1,),0.01,dev
 P=lambda t: ctypes.c_void_p(t.data_ptr())
 for i in range(3):
     if i==2: os.environ['FP8B_GEMM_DEBUG']=str(16+int(os.environ.get('DBG_EXTRA','0')))
-    rc=L.fp8b_scaled_mm(P(A),P(B),P(C),2,M,N,K,N,P(one),1,P(one),1,None,0,None,None,0,2,None); assert rc==0
+    rc=L.fp8b_scaled_mm(P(A),P(B),P(C),2,M,N,K,N,P(one),1,P(one),1,None,0,None,None,0,2,None); assert rc==0, rc
 torch.cuda.synchronize()

@@ -64,7 +64,7 @@ def golden():
 
 
 _TUNE_IDS = {"GEMM_CFG": 16, "GEMV_IMPL": 17, "DYNAMIC_PLAN": 18, "CAST_SHAPE": 19, "GEMM_STORE": 20, "GEMV_UNROLL": 21,
-             "GEMV_BATCH": 22, "AMAX_CAP": 23, "GEMM_RASTER": 24}
+             "GEMV_BATCH": 22, "AMAX_CAP": 23, "GEMM_RASTER": 24, "GEMM_SPLITK": 25}
 
 
 @pytest.fixture

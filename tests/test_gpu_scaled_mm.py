@@ -306,6 +306,63 @@ def test_tcgen05_all_tile_configs(tune, cfg, M, K, N, odt, kw):
     _run_case(M, K, N, odt, ALGO_TCGEN05, seed=cfg + M + N, tol=tol, **kw)
 
 
+@pytest.mark.parametrize("split", [2, 4])
+@pytest.mark.parametrize("M,K,N,odt,kw", [
+    (32, 3072, 3072, torch.bfloat16, {}),                                             # 24 tiles: the shape the plan exists for
+    (256, 3072, 3072, torch.bfloat16, {"bias_dtype": torch.bfloat16}),
+    (100, 4096, 4096, torch.float16, {"per_row_a": True, "per_row_b": True}),
+    (333, 2048, 1000, None, {"bias_dtype": torch.float32, "scale_result": True}),     # ragged M and N, fp32 out
+    (17, 528, 40, None, {"per_row_b": True}),                                         # K tail block, one ragged tile
+    (130, 1024, 260, torch.bfloat16, {"per_row_a": True, "bias_dtype": torch.float16}),
+    (128, 512, 136, torch.float16, {}),                                               # 4 k-blocks: one per CTA when split 4 ways
+    (2048, 1024, 2048, torch.bfloat16, {}),                                           # 256 tiles: more clusters than the GPU holds at once
+])
+def test_tcgen05_split_k(tune, split, M, K, N, odt, kw):
+    """Split-K plan (cluster of 2 / 4 CTAs per 128 x 128 tile, reduce-scatter over distributed shared memory): same
+    tolerances against the oracle as every other plan; bit-identical from run to run (partials are added in rank order)."""
+    tune("GEMM_SPLITK", split)
+    tol = 1e-4 if odt is None else None
+    _run_case(M, K, N, odt, ALGO_TCGEN05, seed=split + M + N, tol=tol, **kw)
+
+
+def test_tcgen05_split_k_is_deterministic_and_automatic(tune):
+    import fp8_mps_native
+    M, K, N = 64, 3072, 3072
+    A = torch.from_numpy(_rand_fp8((M, K), 21)).to(DEV)
+    B = torch.from_numpy(_rand_fp8((N, K), 22)).to(DEV)
+    sa = torch.tensor([0.01], device=DEV); sb = torch.tensor([0.02], device=DEV)
+    L = capi()
+    n0 = L.fp8b_launch_count()
+    auto = fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, torch.bfloat16)       # 24 tiles, 24 k-blocks -> split 4
+    assert L.fp8b_launch_count() - n0 == 1
+    tune("GEMM_SPLITK", 4)
+    runs = [fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, torch.bfloat16).clone() for _ in range(5)]
+    tune("GEMM_SPLITK", 1)
+    plain = fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert all(torch.equal(r, runs[0]) for r in runs)
+    assert torch.equal(auto, runs[0])                          # the automatic rule picked the 4-way split for this shape
+    # the one-CTA-per-tile plan rounds differently (sequential accumulation over all of K) but agrees to bf16 resolution
+    err = o.rel_rmse(to_np(plain), to_np(runs[0]))
+    assert err < 3e-3, err
+
+
+def test_tcgen05_split_k_nan_bytes_and_strided_output(tune):
+    tune("GEMM_SPLITK", 2)
+    rng = np.random.default_rng(14)
+    M, K, N = 96, 1024, 200
+    A = rng.integers(0, 256, (M, K), dtype=np.uint8)
+    B = rng.integers(0, 256, (N, K), dtype=np.uint8)          # ~0.8 % NaN codes
+    sa = np.array([0.02], np.float32); sb = np.array([0.01], np.float32)
+    wide = torch.full((M, 2 * N + 8), 7.0, dtype=torch.bfloat16, device=DEV)
+    out = wide[:, 8:8 + N]                                    # column shard of a wider matrix (ldc > N)
+    rc, C = mm_capi(torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV), torch.from_numpy(sa),
+                    torch.from_numpy(sb), out_dtype=torch.bfloat16, algo=ALGO_TCGEN05, out=out)
+    assert rc == 0
+    _check(out, o.scaled_mm(A, B, sa, sb, out_dtype="bf16"), torch.bfloat16, what="split-K nan+strided")
+    assert bool((wide[:, :8] == 7.0).all()) and bool((wide[:, 8 + N:] == 7.0).all())   # nothing outside the shard
+
+
 @pytest.mark.parametrize("M,K,N,odt,kw", [
     (33, 37, 65, None, {}),
     (64, 256, 128, torch.bfloat16, {"bias_dtype": torch.bfloat16}),
@@ -503,7 +560,7 @@ def test_pdl_chain_sees_fresh_activations(M):
         assert torch.equal(y, ref), f"iteration {it}: chained result differs from the unchained one"
 
 
-@pytest.mark.parametrize("shape", [(256, 512, 384), (300, 1024, 1000)])
+@pytest.mark.parametrize("shape", [(256, 512, 384), (300, 1024, 1000), (64, 2048, 1024)])       # the last one: split-K plan
 def test_pdl_chain_gemm_sees_fresh_operands(shape):
     """The tcgen05 GEMM is launched with programmatic dependent launch too: its prologue runs while the predecessor
     drains, and nothing global may be read before griddepcontrol.wait.  Both operands are re-quantised on the device
