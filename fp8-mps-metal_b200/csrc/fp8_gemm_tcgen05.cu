@@ -1072,7 +1072,11 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
 
     tc_fence_before();
-    if (CG == 2) cluster_sync_all();      // neither CTA may exit (or free TMEM) while its peer still signals it
+    // Neither CTA of a pair may exit (or free TMEM) while its peer still signals it.  The store-ring modes keep the
+    // release / acquire flavour -- the completion signal below is published by another thread than the one that waited for
+    // the bulk stores, and nothing generic is pending there anyway; with st.global epilogues an execution-only barrier
+    // spares the wait for every store of the last tile to be acknowledged.
+    if (CG == 2) { if (is_push<MODE>()) cluster_sync_all(); else cluster_sync_relaxed(); }
     else __syncthreads();
 #ifdef FP8B_PROFILE
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[31] = clock64();          // CTA end
@@ -1749,9 +1753,15 @@ constexpr int kDefaultGemmStore = 2;      // epilogue of plain fp8b_scaled_mm ca
                                           // store (C4: 109.7 vs 112.0 us in the same bench run; falls back to 1 when C is not TMA-storable)
 
 // Tile configuration: 1 = 128x256 one CTA, 2 = 128x128 one CTA, 3 = 256x256 pair, 4 = 256x128 pair, 5 = 256x192 pair.
-static int pick_tile_cfg(const MMArgs& a)
+static int pick_tile_cfg(const MMArgs& a, bool pairs_only = false)
 {
     const int sms = device_info().sm_count;
+    // Small problems (one round of 128 x 128 tiles, or two short ones): one-CTA tiles.  A CTA pair spends ~1 300 more cycles
+    // in its prologue (cluster barrier) and its larger tile leaves a longer exposed epilogue; measured (us, chosen pair
+    // config -> 128 x 128): 512^3 4.9 -> 4.4, 1024^3 6.2 -> 5.7, 2048 x 512 x 2048 8.5 -> 7.2, M=333 K=N=4096 13.1 -> 12.1;
+    // with a long K and two rounds the pairs' cheaper main loop wins again (M=1000 K=N=3072: 12.9 vs 13.9).
+    const long tiles128 = (long)((a.M + kBM - 1) / kBM) * ((a.N + 127) / 128);
+    if (!pairs_only && (tiles128 <= sms || (tiles128 <= 2L * sms && a.K <= 1024))) return 2;
     if (a.M > 128 && a.N > 128) {
         // CTA pairs.  Pick the tile width minimising rounds x time-per-tile.  A tile costs a fixed ~1.5 us (accumulator
         // hand-over, pipeline fill) plus a part proportional to K that was measured at K = 3072 as 10.5 / 9.3 / 8.65 us
@@ -1782,8 +1792,8 @@ int launch_gemm_tcgen05(const MMArgs& a)
     // 256-wide when that still leaves >= ~2 waves of tiles, else 128-wide (finer tail).
     // fp8b_set_option(FP8B_OPT_TUNE_GEMM_CFG) -- a result-neutral tuning knob -- forces one.
     const int forced = tune(kTuneGemmCfg, 0);
-    int cfg = forced ? forced : pick_tile_cfg(a);
     const int mode = a.store_mc & 0xFF;
+    int cfg = forced ? forced : pick_tile_cfg(a, /*pairs_only=*/mode == 2);      // (the round-1 peer-store plan exists for CTA pairs only)
     if (mode == 0 && !forced) {               // plain call: few tiles and a long K -> several CTAs per tile
         const int split = pick_split_k(a);
         if (split == 4) return launch_splitk<4>(a);
