@@ -23,6 +23,10 @@ shard -- no reduction is needed -- and ONE exchange step assembles the (M,N) res
                     (multimem.st), so the exchange overlaps the math tile by tile and no gather or
                     re-layout pass exists.  Needs torch symmetric memory (CUDA, NVLS).
 
+Every plan returns what the un-sharded kernel returns, bit for bit (no reduction crosses ranks), with one exception:
+for problems with very few tiles the un-sharded call may take the library's split-K plan, which rounds differently
+(fp8b_set_option(FP8B_OPT_TUNE_GEMM_SPLITK, 1) turns it off); the sharded kernels never split K.
+
 Shards are contiguous, equal-sized (ceil(N/w) rounded up to `align` columns; the tail shard may be
 short or empty) so the gather can use the fixed-size collective.
 """
