@@ -124,7 +124,8 @@ struct GemmParams {
     const uint8_t* A; const uint8_t* B;      // for the NaN fix-up only
     int M, N, K;
     int num_m_blocks, num_n_blocks, num_k_blocks;
-    int raster_n;                            // tile order: 0 = M fastest (consecutive work items share a B tile), 1 = N fastest
+    int raster_n;                            // tile order: 0 = M fastest (consecutive work items share a B tile), 1 = N fastest,
+                                             // 2 = grouped: N fastest inside bands of kRasterGroup M-blocks (both operands large)
     int stage_tx;                            // bytes one CTA's two TMA loads deliver per stage (the A box is shorter when M < 128)
     int full_tiles;                          // work items [0, full_tiles) are BN-wide tiles ...
     int num_work;                            // ... items [full_tiles, num_work) are half-width tiles (last-wave split)
@@ -304,6 +305,7 @@ __device__ __forceinline__ void lds_v4(uint32_t addr, uint32_t& a, uint32_t& b, 
 // Work item -> tile.  The last, partially filled wave of BN-wide tiles is cut into half-width tiles so that it
 // takes about half a tile time and ends with a half-size epilogue (C4: 768 tiles on 74 CTA pairs = 10 full
 // rounds + 28 tiles -> 56 half tiles in one short round).
+constexpr int kRasterGroup = 8;
 struct TileCoord { int m_blk; int n0; int width; };
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int bn) {
     TileCoord c;
@@ -314,7 +316,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int t, int
         half = u & 1;
     }
     int n_blk;
-    if (p.raster_n) { n_blk = tt % p.num_n_blocks; c.m_blk = tt / p.num_n_blocks; }
+    if (p.raster_n == 2) {
+        // bands of kRasterGroup M-blocks, M fastest inside a band: the ~74 tiles in flight form a near-square patch of the
+        // output, so a wave re-reads ~8 A-blocks + ~9 B-blocks from L2 instead of 2 + all of B
+        const int per_band = kRasterGroup * p.num_n_blocks;
+        const int band = tt / per_band, r = tt - band * per_band;
+        const int m0 = band * kRasterGroup;
+        const int rows = min(kRasterGroup, p.num_m_blocks - m0);
+        c.m_blk = m0 + r % rows;
+        n_blk = r / rows;
+    }
+    else if (p.raster_n) { n_blk = tt % p.num_n_blocks; c.m_blk = tt / p.num_n_blocks; }
     else { c.m_blk = tt % p.num_m_blocks; n_blk = tt / p.num_m_blocks; }
     c.width = half < 0 ? bn : bn >> 1;
     c.n0 = n_blk * bn + (half > 0 ? c.width : 0);
@@ -1554,7 +1566,9 @@ static int launch_tcgen05_cfg(const MMArgs& a)
         const int forced_r = tune(kTuneGemmRaster, 0);
         const size_t b_bytes = (size_t)a.N * a.K, a_bytes = (size_t)a.M * a.K;
         const bool n_fast = b_bytes <= ((size_t)48 << 20) || b_bytes <= a_bytes;
-        p.raster_n = forced_r ? (forced_r == 2) : n_fast;
+        // Both operands too large to sit in L2 beside each other (8192^3: 67 MB each): grouped order.
+        const bool grouped = a_bytes > ((size_t)32 << 20) && b_bytes > ((size_t)32 << 20) && p.num_m_blocks > kRasterGroup;
+        p.raster_n = forced_r ? (forced_r == 3 ? 2 : forced_r == 2) : grouped ? 2 : n_fast;
     }
     const int tiles_all = p.num_m_blocks * p.num_n_blocks;
     const int workers_cap = device_info().sm_count / CG;

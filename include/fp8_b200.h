@@ -93,7 +93,8 @@ FP8B_API uint64_t fp8b_launch_count(void);
  *                              CAST_SHAPE    cast launch shape: 1 = small tiles, 2 = big tiles
  *                              GEMM_STORE    tcgen05 epilogue: 1 = st.global from the epilogue warps, 2 = TMA store
  *                              GEMV_UNROLL / GEMV_BATCH / AMAX_CAP   load batching of the GEMV kernels / amax grid cap
- *                              GEMM_RASTER   tcgen05 tile order: 1 = M fastest, 2 = N fastest (whole output rows complete together)
+ *                              GEMM_RASTER   tcgen05 tile order: 1 = M fastest, 2 = N fastest (whole output rows complete together),
+ *                                            3 = N fastest inside bands of 8 M-blocks (L2 reuse when both operands are large)
  *                              GEMM_SPLITK   split-K plan for problems with few tiles: 1 = never, 2 / 4 = that many CTAs per tile.
  *                                            (The one knob that is not bit-neutral: partial sums over K ranges are added in
  *                                            rank order, so results are deterministic but rounded differently from the

@@ -154,13 +154,13 @@ def test_push_ragged_column_block(tune, store):
 
 @pytest.mark.parametrize("M,K,N,odt", [(2304, 256, 2560, torch.bfloat16), (1000, 512, 3000, torch.float16), (300, 128, 520, torch.float32)])
 def test_tile_raster_orders_agree(tune, M, K, N, odt):
-    """FP8B_OPT_TUNE_GEMM_RASTER: M-fastest and N-fastest tile orders (incl. the split last wave) give the same bits, with
-    both epilogues."""
+    """FP8B_OPT_TUNE_GEMM_RASTER: M-fastest, N-fastest and banded (8 M-blocks per band; 2304 rows = one full band + one
+    short one) tile orders, incl. the split last wave, give the same bits, with both epilogues."""
     A, B = _bytes((M, K), 21), _bytes((N, K), 22)
     tA, tB = torch.from_numpy(A).to(DEV), torch.from_numpy(B).to(DEV)
     s = torch.full((1,), 0.01, device=DEV)
     outs = []
-    for raster in (1, 2):
+    for raster in (1, 2, 3):
         for store in (1, 2):
             tune("GEMM_RASTER", raster)
             tune("GEMM_STORE", store)
