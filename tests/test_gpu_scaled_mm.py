@@ -347,6 +347,30 @@ def test_tcgen05_split_k_is_deterministic_and_automatic(tune):
     assert err < 3e-3, err
 
 
+def test_tcgen05_split_k_random_shapes(tune):
+    """Stress of the cluster protocol (DSMEM bulk copies, receive barriers, short A box, ragged edges): 80 random shapes,
+    both split factors, fp32 out, against the one-CTA-per-tile plan of the same kernel family -- the two differ only in
+    the rounding of the partial sums (a few 1e-6 rel-RMSE at K = 6000; bound 1e-5); a lost or early-read block would be off by orders of magnitude.
+    Every split result must also repeat bit for bit."""
+    import fp8_mps_native
+    rng = np.random.default_rng(2024)
+    sa = torch.tensor([0.01], device=DEV); sb = torch.tensor([0.02], device=DEV)
+    for case in range(80):
+        M = int(rng.integers(17, 400)); N = int(rng.integers(8, 1500)); K = 16 * int(rng.integers(32, 400))
+        split = 2 if case % 2 else 4
+        A = torch.from_numpy(_rand_fp8((M, K), 1000 + case)).to(DEV)
+        B = torch.from_numpy(_rand_fp8((N, K), 2000 + case)).to(DEV)
+        tune("GEMM_SPLITK", 1)
+        plain = fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, None, algo=ALGO_TCGEN05)
+        tune("GEMM_SPLITK", split)
+        y1 = fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, None, algo=ALGO_TCGEN05).clone()
+        y2 = fp8_mps_native.fp8_scaled_mm_fused(A, B, sa, sb, None, None, None, algo=ALGO_TCGEN05)
+        torch.cuda.synchronize()
+        assert torch.equal(y1, y2), (case, M, K, N, split)
+        err = o.rel_rmse(to_np(y1), to_np(plain))
+        assert err <= 1e-5, (case, M, K, N, split, err)
+
+
 def test_tcgen05_split_k_nan_bytes_and_strided_output(tune):
     tune("GEMM_SPLITK", 2)
     rng = np.random.default_rng(14)
