@@ -306,6 +306,23 @@ def test_tcgen05_all_tile_configs(tune, cfg, M, K, N, odt, kw):
     _run_case(M, K, N, odt, ALGO_TCGEN05, seed=cfg + M + N, tol=tol, **kw)
 
 
+@pytest.mark.parametrize("odt", [None, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("kind", range(8))
+def test_tcgen05_every_epilogue_term_combination(tune, kind, odt):
+    """The TMA-store epilogue compiles one copy of its tile loop per combination of optional terms (per-column scale_b,
+    bias, scale_result): run each of the eight, for every output dtype, on a shape with a ragged column edge (the
+    out-of-line edge loads), several tiles per CTA pair and a K tail."""
+    tune("GEMM_SPLITK", 1)
+    kw = {"per_row_b": bool(kind & 1), "scale_result": bool(kind & 4)}
+    if kind & 2:
+        kw["bias_dtype"] = torch.float32 if odt is None else odt
+    M, K, N = 520, 400, 40 * 8 + 24 if odt is None else 1160                # N * esz % 16 == 0 -> TMA-store epilogue
+    tol = 1e-4 if odt is None else None
+    for cfg in (2, 4):
+        tune("GEMM_CFG", cfg)
+        _run_case(M, K, N, odt, ALGO_TCGEN05, seed=50 + kind, per_row_a=bool(kind & 1), tol=tol, **kw)
+
+
 @pytest.mark.parametrize("split", [2, 4])
 @pytest.mark.parametrize("M,K,N,odt,kw", [
     (32, 3072, 3072, torch.bfloat16, {}),                                             # 24 tiles: the shape the plan exists for
