@@ -691,7 +691,7 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 // kStTma.  Software-pipelined: the tcgen05.ld of chunk c+1 is in flight while chunk c is scaled, packed and
                 // staged (two register sets).  Which optional epilogue terms exist (KIND) is a compile-time constant of the
                 // whole tile loop -- one of eight copies runs -- and the cold paths (NaN fix-up, ragged column edge) are out
-                // of line, so the hot loop is short and contiguous: a 128 x 256 accumulator is drained in 3 700 cycles
+                // of line, so the hot loop is short and contiguous: a 128 x 256 accumulator is drained in 4 900 cycles
                 // instead of 8 100-12 000.  That matters where the epilogue is exposed: the last tile of every CTA, i.e.
                 // all of a small problem.
                 auto run_tiles = [&](auto kind_c) {
@@ -793,13 +793,13 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         tmem_ld_x32(t_row, ra);
 #pragma unroll 1
                         for (int ch = 0; ch < nch; ch += 2) {
-                            tmem_ld_wait_for(ra);
-                            __syncwarp();                   // lanes may have diverged in chunk() (row mask, NaN fix-up)
+                            __syncwarp();                   // lanes may have diverged in chunk() (row mask, NaN fix-up);
+                            tmem_ld_wait_for(ra);           // tcgen05.wait / .ld are warp-collective (.sync.aligned)
                             if (ch + 1 < nch) tmem_ld_x32(t_row + (uint32_t)((ch + 1) * 32), rb); else release_acc();
                             chunk(ch * 32, ra);
                             if (ch + 1 < nch) {
-                                tmem_ld_wait_for(rb);
                                 __syncwarp();
+                                tmem_ld_wait_for(rb);
                                 if (ch + 2 < nch) tmem_ld_x32(t_row + (uint32_t)((ch + 2) * 32), ra); else release_acc();
                                 chunk((ch + 1) * 32, rb);
                             }
@@ -1122,9 +1122,9 @@ fp8_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // A problem with fewer 128 x 128 tiles than SMs leaves most of the GPU idle and every busy SM walks the whole of K alone
 // (M = 32, K = N = 3072: 24 CTAs, 6 100 cycles of MMAs each).  Here a thread-block CLUSTER of S CTAs shares one tile: CTA r
 // accumulates k-blocks [r, r+1) * KB / S into its own TMEM accumulator, then the cluster reduce-scatters over distributed
-// shared memory -- CTA r sends column slice j of its partial tile to CTA j (st.shared::cluster) and receives slice r of
-// every partial -- and each CTA sums its slice in rank order (deterministic), applies the epilogue and stores it.  The
-// reduction costs 64 KB of DSMEM traffic per CTA and spreads the epilogue over the S CTAs as well.
+// shared memory -- CTA r sends column slice j of its partial tile to CTA j (bulk copies, shared memory to the peer's shared
+// memory) and receives slice r of every partial -- and each CTA sums its slice in rank order (deterministic), applies the
+// epilogue and stores it.  The reduction costs 64 KB of DSMEM traffic per CTA and spreads the epilogue over the S CTAs.
 //   warps 0..3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer, warp 5 MMA issuer; one tile per cluster.
 constexpr int kSkStages = 5;
 constexpr int kSkStageBytes = 2 * kBM * kBK;                     // A 128 x 128 B + B 128 x 128 B
@@ -1167,9 +1167,7 @@ __global__ void __launch_bounds__(kSkThreads, 1)
 fp8_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const SplitKParams p)
 {
     constexpr int kSlice = 128 / S;                  // output columns this CTA finishes
-    constexpr int kPieces = kSlice / 4;              // 16-byte pieces per row of a receive slot (>= 8)
-    constexpr int kSlotBytes = kBM * kSlice * 4;
-    static_assert(S == 2 || S == 4, "slices must be whole 32-column TMEM chunks");
+    static_assert(S == 2 || S == 4, "slices must be whole 32-column TMEM chunks (and >= 8 16-byte pieces per row for the swizzle)");
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
